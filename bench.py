@@ -1,0 +1,390 @@
+#!/usr/bin/env python
+"""bench.py -- member-years/s of the classic-EBM hysteresis ensemble (BASELINE.json config C4) on B200.
+
+One "step" = one full pass of the hot path over the workload: N_members x 200 simulated years of the
+classic EBM (nx=100, nt=2000), L0 diagnostics for every member-year.
+
+  value  : device-resident throughput (inputs already in HBM, ebm_classic_run_device on torch's stream),
+           CUDA-event timed, max over ranks; plus the NCCL gather of the diagnostics when N > 1.
+  e2e    : same metric through the host-buffer C-ABI call ebm_classic_run (pinned host inputs, H2D, kernel,
+           D2H of diagnostics + final state inside the timed region).
+  roofline : FP64.  achieved = 37 FLOP/cell-step x nx x nt x member-years of one launch / its duration;
+           peak = DFMA throughput measured in this run (MEASURED_PEAKS.json has no FP64 entry).
+  cpu_baseline : the C oracle (a port of the reference's algorithm, tridiagonal solve) with OpenMP on all
+           host cores, on a bounded sample of the same workload.
+
+`--impl reference` times that CPU implementation alone (rank 0 only).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOP_PER_CELL_STEP = {"classic": 37.0, "miz": 173.0}
+NOMINAL_FP64_TFLOPS = 37.2                               # 148 SM x 64 FMA/clk x 2 x 1.965 GHz
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="classic", choices=["classic", "miz"])
+    ap.add_argument("--members", type=int, default=0, help="members per GPU (default: 65536 classic, 131072 miz)")
+    ap.add_argument("--years", type=int, default=0, help="simulated years (default: 200 classic, 50 miz)")
+    ap.add_argument("--cpu-sample-members", type=int, default=0)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------- workloads
+def classic_workload(ebm, nmem_total, offset, count, years):
+    """C4: F_m = -20 + 40*(m mod H)/(H-1); first half warm start, second half cold start (H = nmem_total/2)."""
+    st = ebm.SpaceTime(100, 2000, years)
+    p = ebm.default_parameters("Classic")
+    prow = np.array([p[k] for k in ebm.CLASSIC_PAR_ORDER])
+    H = max(nmem_total // 2, 1)
+    m = np.arange(offset, offset + count)
+    F = -20.0 + 40.0 * (m % H) / max(H - 1, 1)
+    warm = m < H
+    par = np.repeat(prow[None, :], count, axis=0)
+    forc = np.zeros((count, 10))
+    forc[:, 0] = forc[:, 1] = forc[:, 2] = F
+    E0 = np.where(warm[:, None], 98.0, -9.5) * np.ones((count, st.nx))
+    Tg0 = np.where(warm[:, None], 10.0, -10.0) * np.ones((count, st.nx))
+    return st, par, forc, (E0, Tg0)
+
+
+def miz_workload(ebm, nmem_total, offset, count, years):
+    """C5: 16^5 tensor grid over (D, B, ai, k, m1) when nmem_total = 2^20 (row-major); zero init, F = 0."""
+    st = ebm.SpaceTime(180, 2000, years, "sin")
+    p = ebm.default_parameters("MIZ")
+    order = list(ebm.MIZ_PAR_ORDER)
+    prow = np.array([p[k] for k in order])
+    par = np.repeat(prow[None, :], count, axis=0)
+    m = np.arange(offset, offset + count)
+    n = max(int(round(nmem_total ** 0.2)), 1)
+    idx = [(m // n ** (4 - q)) % n for q in range(5)]
+    lin = lambda lo, hi, i: lo + (hi - lo) * i / max(n - 1, 1)
+    par[:, order.index("D")] = lin(0.45, 0.75, idx[0])
+    par[:, order.index("B")] = lin(1.8, 2.4, idx[1])
+    par[:, order.index("ai")] = lin(0.35, 0.45, idx[2])
+    par[:, order.index("k")] = lin(1.5, 2.5, idx[3])
+    par[:, order.index("m1")] = p["m1"] * lin(0.5, 2.0, idx[4])
+    forc = np.zeros((count, 10))
+    z = np.zeros((count, st.nx))
+    return st, par, forc, (z, z, z, z, z)
+
+
+# ----------------------------------------------------------------------------- clocks sampling
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for k, nme in enumerate(names):
+                if len(r) > 2 + k and r[2 + k].lower().startswith("active"):
+                    reasons.add(nme)
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        pw = [float(r[6]) for r in self.rows if len(r) > 6 and r[6].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx[0] if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm), "power_w_max": max(pw) if pw else None}
+
+
+# ----------------------------------------------------------------------------- CPU arm
+def cpu_run(workload, nmem_total, years, sample_members, threads):
+    """Oracle (port of the reference algorithm) with OpenMP over members on a strided sample."""
+    import ebm_b200 as ebm
+    import oracle
+    stride = max(nmem_total // sample_members, 1)
+    idx = np.arange(0, nmem_total, stride)[:sample_members]
+    if workload == "classic":
+        st, par, forc, (E0, Tg0) = classic_workload(ebm, nmem_total, 0, nmem_total, years)
+        t0 = time.perf_counter()
+        oracle.classic_run(st.x, st.t, years, st.winter.inx, st.summer.inx, par[idx], forc[idx], E0[idx], Tg0[idx],
+                           want_seasonal=True, nthreads=threads)
+    else:
+        st, par, forc, init = miz_workload(ebm, nmem_total, 0, nmem_total, years)
+        t0 = time.perf_counter()
+        oracle.miz_run(st.x, st.t, years, st.winter.inx, st.summer.inx, st.grid_kind, par[idx], forc[idx],
+                       *[a[idx] for a in init], want_seasonal=True, nthreads=threads)
+    dt = time.perf_counter() - t0
+    return len(idx) * years / dt, dt, f"{len(idx)} members (stride {stride}) x {years} years, seasonal sampling on"
+
+
+def reference_arm(args, nmem, years):
+    import oracle
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = oracle.max_threads()
+    sample = args.cpu_sample_members or (8 * threads if args.workload == "classic" else 2 * threads)
+    yrs = years
+    vals = []
+    for i in range(args.warmup + args.steps):
+        v, dt, desc = cpu_run(args.workload, nmem, yrs, sample, threads)
+        if i >= args.warmup:
+            vals.append((v, dt))
+    value = sum(v * dt for v, dt in vals) / sum(dt for _, dt in vals)   # member-years / seconds over the K steps
+    ms = 1e3 * sum(dt for _, dt in vals) / len(vals)
+    line = {
+        "impl": "reference", "metric": "member_years_per_sec", "value": value, "unit": "member-years/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args.workload, nmem, years, args.gpus),
+        "cpu_baseline": {"value": value, "unit": "member-years/s", "cores": threads, "kind": "port", "sample": desc,
+                         "note": "C oracle restating src/classic.jl / src/miz.jl (tridiagonal solve instead of the "
+                                 "reference's dense LU); Julia is not installed, the reference itself cannot run"},
+        "e2e": {"value": value, "unit": "member-years/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(workload, nmem, years, gpus):
+    if workload == "classic":
+        return {"workload": "C4 classic-EBM hysteresis ensemble: F=-20..+20 W/m^2, warm+cold start branches",
+                "members_per_gpu": nmem, "members_total": nmem * gpus, "years": years, "nx": 100, "nt": 2000,
+                "outputs": "L0 diagnostics (3 seasons x 4 scalars per member-year) + final state",
+                "l2": "flushed between timed iterations (256 MiB write); state is register-resident in any case"}
+    return {"workload": "C5 MIZ parameter-sweep ensemble over (D,B,ai,k,m1), zero init, F=0",
+            "members_per_gpu": nmem, "members_total": nmem * gpus, "years": years, "nx": 180, "nt": 2000,
+            "grid": "sin", "outputs": "L0 diagnostics + final state",
+            "l2": "flushed between timed iterations (256 MiB write)"}
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def main():
+    args = parse()
+    nmem = args.members or (65536 if args.workload == "classic" else 131072)
+    years = args.years or (200 if args.workload == "classic" else 50)
+    if args.impl == "reference":
+        reference_arm(args, nmem, years)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import ebm_b200 as ebm
+    from ebm_b200 import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+
+    total = nmem * world
+    build = classic_workload if args.workload == "classic" else miz_workload
+    st, par, forc, init = build(ebm, total, rank * nmem, nmem, years)
+    nx, nt = st.nx, st.nt
+    grid = _lib.make_grid(st)
+    opt = _lib.make_options(device=local, lastonly=True, field_stride=0)
+
+    # ---- device-resident inputs (member index fastest), allocated by torch
+    f64 = torch.float64
+    d_par = torch.from_numpy(np.ascontiguousarray(par.T)).to(dev)
+    d_forc = torch.from_numpy(np.ascontiguousarray(forc.T)).to(dev)
+    d_init = [torch.from_numpy(np.ascontiguousarray(a.T)).to(dev) for a in init]
+    nstate = len(init) + (1 if args.workload == "miz" else 0)
+    d_state = [torch.empty((nx, nmem), dtype=f64, device=dev) for _ in range(nstate)]
+    d_diag = torch.full((nmem, years, 3, 4), float("nan"), dtype=f64, device=dev)
+    d_flags = torch.zeros(nmem, dtype=torch.int32, device=dev)
+    d_i64 = torch.zeros((2, nmem), dtype=torch.int64, device=dev)
+    gathered = torch.empty((world, nmem, years, 3, 4), dtype=f64, device=dev) if (world > 1 and rank == 0) else None
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream()
+
+    if args.workload == "classic":
+        dargs = _lib.ClassicDeviceArgs(nmem, d_par.data_ptr(), d_forc.data_ptr(), d_state[0].data_ptr(),
+                                       d_state[1].data_ptr(), d_diag.data_ptr(), None, None, d_flags.data_ptr())
+        run_dev = lambda: _lib.check(lib.ebm_classic_run_device(C.byref(grid), C.byref(dargs), C.byref(opt),
+                                                                C.c_void_p(stream.cuda_stream)))
+    else:
+        dargs = _lib.MizDeviceArgs(nmem, d_par.data_ptr(), d_forc.data_ptr(), *[t.data_ptr() for t in d_state],
+                                   d_diag.data_ptr(), None, None, d_i64[0].data_ptr(), d_i64[1].data_ptr(),
+                                   d_flags.data_ptr())
+        run_dev = lambda: _lib.check(lib.ebm_miz_run_device(C.byref(grid), C.byref(dargs), C.byref(opt),
+                                                            C.c_void_p(stream.cuda_stream)))
+
+    kern_ms = []
+
+    def step(timed):
+        flush.fill_(1)                                     # L2 flush
+        for k, a in enumerate(d_init):                     # restore the batch's initial state (device copy)
+            d_state[k].copy_(a)
+        if args.workload == "miz":
+            d_state[-1].zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        run_dev()
+        e1.record(stream)
+        if world > 1:                                      # NCCL over NVLink: gather the ensemble diagnostics
+            dist.gather(d_diag, list(gathered.unbind(0)) if rank == 0 else None, dst=0)
+        if timed:
+            kern_ms.append((e0, e1))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step(False)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = lib.ebm_launch_count()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record(stream)
+    for _ in range(args.steps):
+        step(True)
+    t1.record(stream)
+    barrier()
+    launches = lib.ebm_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = t0.elapsed_time(t1)
+    k_ms = float(np.mean([a.elapsed_time(b) for a, b in kern_ms]))
+    if world > 1:
+        tt = torch.tensor([ms_total, k_ms], dtype=f64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_total, k_ms = tt.tolist()
+    bad = int(d_flags.max().item())
+    ms_per_step = ms_total / args.steps
+    value = total * years / (ms_per_step * 1e-3)
+
+    # ---- roofline of the dominant kernel (this rank's launch)
+    flop_launch = FLOP_PER_CELL_STEP[args.workload] * nx * nt * float(years) * nmem
+    achieved = flop_launch / (k_ms * 1e-3) / 1e12
+    peak_tf, peak_mhz = ebm.fp64_peak(local)
+    diag_bytes = d_diag.numel() * 8
+    roof = {"bound": "fp64", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+            "traffic": None,
+            "peak_source": "measured in this run by ebm_fp64_peak (dependent-free DFMA chains); "
+                           "MEASURED_PEAKS.json has no FP64 entry",
+            "peak_nominal": NOMINAL_FP64_TFLOPS, "frac_of_nominal": achieved / NOMINAL_FP64_TFLOPS,
+            "kernel": "classic_bands_kernel" if args.workload == "classic" else "miz_kernel",
+            "kernel_ms": k_ms, "algorithmic_flop_per_cell_step": FLOP_PER_CELL_STEP[args.workload],
+            "hbm_output_stream": {"bytes_per_launch": diag_bytes, "achieved_gbs": diag_bytes / (k_ms * 1e-3) / 1e9,
+                                  "peak_gbs": _measured_hbm()}}
+
+    # ---- end to end through the host-buffer C ABI (pinned inputs, H2D + kernel + D2H timed)
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(args, ebm, lib, _lib, st, par, forc, init, nmem, years, local, world, total)
+
+    cpu = None
+    if rank == 0 and not args.no_cpu:
+        import oracle
+        thr = oracle.max_threads()
+        sample = args.cpu_sample_members or (8 * thr if args.workload == "classic" else 2 * thr)
+        v, dt, desc = cpu_run(args.workload, total, years, sample, thr)
+        cpu = {"value": v, "unit": "member-years/s", "cores": thr, "kind": "port", "sample": desc, "seconds": dt}
+
+    if rank == 0:
+        line = {
+            "metric": "member_years_per_sec", "value": value, "unit": "member-years/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args.workload, nmem, years, world),
+            "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "nan_flags": bad,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _measured_hbm():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return json.load(fh).get("hbm_gbs")
+    except Exception:
+        return 6650.0
+
+
+def run_e2e(args, ebm, lib, _lib, st, par, forc, init, nmem, years, local, world, total):
+    import torch
+    import torch.distributed as dist
+    nx = st.nx
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    h_par, h_forc = pin(par), pin(forc)
+    h_init = [pin(a) for a in init]
+    h_diag = torch.empty((nmem, years, 3, 4), dtype=torch.float64).pin_memory()
+    nfin = len(init) + (1 if args.workload == "miz" else 0)
+    h_fin = [torch.empty((nmem, nx), dtype=torch.float64).pin_memory() for _ in range(nfin)]
+    grid = _lib.make_grid(st)
+    opt = _lib.make_options(device=local, lastonly=True, field_stride=0)
+    P = lambda t: C.cast(t.data_ptr(), C.POINTER(C.c_double))
+    if args.workload == "classic":
+        out = _lib.ClassicOutputs(P(h_diag), None, None, P(h_fin[0]), P(h_fin[1]), None)
+        call = lambda: _lib.check(lib.ebm_classic_run(C.byref(grid), nmem, P(h_par), P(h_forc), P(h_init[0]), P(h_init[1]),
+                                                      C.byref(opt), C.byref(out)))
+    else:
+        out = _lib.MizOutputs(P(h_diag), None, None, *[P(t) for t in h_fin], None, None, None)
+        call = lambda: _lib.check(lib.ebm_miz_run(C.byref(grid), nmem, P(h_par), P(h_forc), *[P(t) for t in h_init], None,
+                                                  C.byref(opt), C.byref(out)))
+    h2d = sum(t.numel() * 8 for t in [h_par, h_forc] + h_init)
+    d2h = h_diag.numel() * 8 + sum(t.numel() * 8 for t in h_fin)
+    call()  # warm
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    n = max(1, min(args.steps, 2))
+    t0 = time.perf_counter()
+    for _ in range(n):
+        call()
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / n
+    if world > 1:
+        tt = torch.tensor([dt], dtype=torch.float64, device=torch.device("cuda", local))
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+    return {"value": total * years / dt, "unit": "member-years/s", "h2d_bytes_per_step": int(h2d),
+            "d2h_bytes_per_step": int(d2h), "seconds_per_step": dt, "steps": n,
+            "api": "ebm_classic_run (host-buffer C ABI)" if args.workload == "classic" else "ebm_miz_run (host-buffer C ABI)",
+            "result_check": {"mean_T_last_year_member0": float(h_diag[0, -1, 2, 0])}}
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,20 @@
+"""B200-native ensemble integrator for the time-stepping path of EnergyBalanceModel.jl.
+
+Importable as ``ebm_b200`` (see the shim package of that name; this directory carries the
+reference's name).  The host-side names mirror the reference's exports
+(src/EnergyBalanceModel.jl:79-82) for this path: ``Vec``-like NumPy arrays, ``Collection``,
+``SpaceTime``, ``Forcing``, ``Solutions``, ``integrate``, ``default_parameters``.  All arithmetic
+runs in ``lib/libebm_cuda.so`` (hand-written CUDA for sm_100a) behind the C ABI in
+``include/ebm_cuda.h``; without the library or without a GPU every compute call raises.
+"""
+from .types import (CLASSIC_PAR_ORDER, CLASSIC_VARS, MIZ_PAR_ORDER, MIZ_VARS, Collection, Forcing, Solutions,
+                    SpaceTime, classic_paramset, default_parameters, default_parval, hemispheric_mean,
+                    miz_paramset)
+from .integrate import EnsembleResult, fp64_peak, integrate, integrate_ensemble, model_name, step
+from . import _lib, build  # noqa: F401
+
+__all__ = [
+    "Collection", "SpaceTime", "Forcing", "Solutions", "integrate", "integrate_ensemble", "step",
+    "default_parameters", "default_parval", "miz_paramset", "classic_paramset", "hemispheric_mean",
+    "EnsembleResult", "fp64_peak", "model_name", "CLASSIC_PAR_ORDER", "MIZ_PAR_ORDER", "CLASSIC_VARS", "MIZ_VARS",
+]

@@ -1,0 +1,115 @@
+// ebm_internal.cuh -- shared declarations of libebm_cuda.so (not part of the ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "ebm_cuda.h"
+
+// ----------------------------------------------------------------------------- error plumbing
+void ebm_set_error(const char* fmt, ...);
+void ebm_count_launch(int n = 1);
+
+#define EBM_CUDA_TRY(expr)                                                                        \
+  do {                                                                                            \
+    cudaError_t _e = (expr);                                                                      \
+    if (_e != cudaSuccess) {                                                                      \
+      ebm_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__);  \
+      return (_e == cudaErrorMemoryAllocation) ? EBM_ERR_OOM : EBM_ERR_CUDA;                      \
+    }                                                                                             \
+  } while (0)
+
+// ----------------------------------------------------------------------------- device grid tables
+// Everything that depends only on SpaceTime (x, t, nx, nt), computed once on the host in IEEE
+// double with the reference's association order, cached per device (ebm_capi.cu).
+struct EbmGridTables {
+  int nx, nt, kind;
+  const double* x;       // [nx]      st.x
+  const double* x2;      // [nx]      x*x
+  const double* lam_lo;  // [nx]      get_diffop lambda between j-1 and j (0 at j=0)        infrastructure.jl:482-488
+  const double* lam_hi;  // [nx]      lambda between j and j+1 (0 at j=nx-1)
+  const double* wts;     // [nx]      hemispheric_mean trapezoid weight of cell j            utilities.jl:397-403
+  const double* ctab;    // [nt+1]    cos(2*pi*t_i), entry nt := entry 0                      classic.jl:24-25
+  // generic flux-form stencil (infrastructure.jl:509-519)
+  const double* diffx;   // [nx+1]
+  const double* mxxph;   // [nx]
+  const double* mxxmh;   // [nx]
+  const double* phmmh;   // [nx]
+};
+
+// ----------------------------------------------------------------------------- kernel argument blocks
+struct ClassicKArgs {
+  int nx, nt, dur, W;
+  long long nmem;
+  int year0, nyears;             // integrate years [year0, year0+nyears), 0-based
+  int winter_inx, summer_inx, lastonly, field_stride, all_const_forcing;
+  int uniform_split;             // 1: classic_uniform.cu integrates parameter-uniform 32-member groups, classic_bands.cu the rest
+  EbmGridTables g;
+  const double* par;             // [15][nmem]
+  const double* forc;            // [10][nmem]
+  double* E; double* Tg;         // [nx][nmem]
+  double* diag; double* seasonal; double* raw; int* flags;
+};
+
+struct MizKArgs {
+  int nx, nt, dur;
+  long long nmem;
+  int year0, nyears;
+  int winter_inx, summer_inx, lastonly, field_stride, all_const_forcing;
+  int maxit; double tol;
+  EbmGridTables g;
+  const double* par;             // [22][nmem]
+  const double* forc;            // [10][nmem]
+  double *Ei, *Ew, *h, *D, *phi, *T0;   // [nx][nmem]
+  double* diag; double* seasonal; double* raw;
+  long long* newton_iters; long long* nonconv; int* flags;
+};
+
+// launchers (each returns an EBM_* status; kernels are enqueued on `stream`)
+int ebm_launch_classic_bands(const ClassicKArgs& a, cudaStream_t stream);
+int ebm_launch_classic_uniform(const ClassicKArgs& a, int variant, cudaStream_t stream);
+int ebm_classic_uniform_max_nx();
+int ebm_launch_classic_strict(const ClassicKArgs& a, cudaStream_t stream);
+int ebm_launch_classic_single_step(const EbmGridTables& g, const double* par15, int ti, double f,
+                                   double* E, double* Tg, double* T, double* h, cudaStream_t stream);
+int ebm_launch_miz(const MizKArgs& a, int strict, cudaStream_t stream);
+int ebm_launch_miz_single_step(const EbmGridTables& g, const double* par22, int ti, double f, double tol, int maxit,
+                               double* Ei, double* Ew, double* h, double* D, double* phi, double* T0,
+                               double* vars_out, int* iters, cudaStream_t stream);
+int ebm_launch_transpose(const double* src, double* dst, long long rows, long long cols, cudaStream_t stream);
+int ebm_launch_fill(double* dst, long long n, double v, cudaStream_t stream);
+int ebm_run_fp64_peak(int device, double* tflops, double* mhz);
+
+// ----------------------------------------------------------------------------- small device helpers
+// Forcing call (src/infrastructure.jl:294-307).  fr = base, peak, cool, rate_up, rate_down, d1..d5.
+__device__ __forceinline__ double ebm_forcing_eval(double base, double peak, double cool, double rup, double rdown,
+                                                   double d2, double d3, double d4, double d5, double T) {
+  if (T < d2) return base;
+  if (T < d3) return base + rup * (T - d2);
+  if (T < d4) return peak;
+  if (T < d5) return peak + rdown * (T - d4);
+  return cool;
+}
+
+// SpaceTime.T[tinx] (1-based): correctly rounded (2*tinx-1)/(2*nt)  (infrastructure.jl:130, TwicePrecision range)
+__device__ __forceinline__ double ebm_global_time(long long tinx, int nt) {
+  return __ddiv_rn((double)(2 * tinx - 1), (double)(2LL * nt));
+}
+
+// Do the members of the 32-aligned group that contains this CTA's members share all classic parameters bit for
+// bit?  Called by every thread of the CTA (contains a barrier); mi = member slot of the thread, MW = members per
+// CTA (a divisor of 32).  The uniform and the general kernel use this same rule to split an ensemble between them.
+template <int MW>
+__device__ __forceinline__ bool ebm_classic_group_uniform(const double* __restrict__ par, long long nmem,
+                                                          long long m_first, int mi) {
+  const long long g0 = (m_first / 32) * 32;
+  bool same = true;
+#pragma unroll 1
+  for (int r = 0; r < 32 / MW; ++r) {
+    long long mm = g0 + mi + (long long)r * MW;
+    if (mm >= nmem) mm = nmem - 1;
+    for (int k = 0; k < EBM_CLASSIC_NPAR; ++k)
+      same = same && (par[(long long)k * nmem + mm] == par[(long long)k * nmem + g0]);
+  }
+  return __syncthreads_and(same) != 0;
+}

@@ -1,0 +1,101 @@
+// util_kernels.cu -- layout helpers and the FP64 roof microbenchmark.
+#include "ebm_internal.cuh"
+
+namespace {
+
+// [rows][cols] -> [cols][rows], 32x32 tiles through shared memory (coalesced on both sides)
+__global__ void transpose_kernel(const double* __restrict__ src, double* __restrict__ dst, long long rows, long long cols) {
+  __shared__ double tile[32][33];
+  const long long c0 = (long long)blockIdx.x * 32, r0 = (long long)blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const long long r = r0 + i, c = c0 + threadIdx.x;
+    if (r < rows && c < cols) tile[i][threadIdx.x] = src[r * cols + c];
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const long long c = c0 + i, r = r0 + threadIdx.x;
+    if (r < rows && c < cols) dst[c * rows + r] = tile[threadIdx.x][i];
+  }
+}
+
+__global__ void fill_kernel(double* dst, long long n, double v) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    dst[i] = v;
+}
+
+// FP64 FMA roof: 8 independent dependent-chains per thread, 8 warps per SMSP-quad worth of TLP.
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters, double a, double b, long long* cycles) {
+  double acc0 = threadIdx.x, acc1 = acc0 + 1, acc2 = acc0 + 2, acc3 = acc0 + 3;
+  double acc4 = acc0 + 4, acc5 = acc0 + 5, acc6 = acc0 + 6, acc7 = acc0 + 7;
+  const long long t0 = clock64();
+#pragma unroll 4
+  for (int i = 0; i < iters; ++i) {
+    acc0 = fma(acc0, a, b); acc1 = fma(acc1, a, b); acc2 = fma(acc2, a, b); acc3 = fma(acc3, a, b);
+    acc4 = fma(acc4, a, b); acc5 = fma(acc5, a, b); acc6 = fma(acc6, a, b); acc7 = fma(acc7, a, b);
+  }
+  const long long t1 = clock64();
+  const double r = ((acc0 + acc1) + (acc2 + acc3)) + ((acc4 + acc5) + (acc6 + acc7));
+  if (r == 123.456) out[0] = r;  // keep the chains alive
+  if (threadIdx.x == 0 && blockIdx.x == 0) cycles[0] = t1 - t0;
+}
+
+}  // namespace
+
+int ebm_launch_transpose(const double* src, double* dst, long long rows, long long cols, cudaStream_t stream) {
+  if (rows <= 0 || cols <= 0) return EBM_OK;
+  dim3 block(32, 8);
+  dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32));
+  if (grid.y > 65535) { ebm_set_error("transpose: too many rows (%lld)", rows); return EBM_ERR_INVALID; }
+  transpose_kernel<<<grid, block, 0, stream>>>(src, dst, rows, cols);
+  EBM_CUDA_TRY(cudaGetLastError());
+  ebm_count_launch();
+  return EBM_OK;
+}
+
+int ebm_launch_fill(double* dst, long long n, double v, cudaStream_t stream) {
+  if (n <= 0) return EBM_OK;
+  fill_kernel<<<1184, 256, 0, stream>>>(dst, n, v);
+  EBM_CUDA_TRY(cudaGetLastError());
+  ebm_count_launch();
+  return EBM_OK;
+}
+
+int ebm_run_fp64_peak(int device, double* tflops, double* mhz) {
+  if (device >= 0) EBM_CUDA_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  int dev = 0;
+  EBM_CUDA_TRY(cudaGetDevice(&dev));
+  EBM_CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+  double* out = nullptr; long long* cyc = nullptr;
+  EBM_CUDA_TRY(cudaMalloc(&out, sizeof(double)));
+  EBM_CUDA_TRY(cudaMalloc(&cyc, sizeof(long long)));
+  const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 16;
+  cudaEvent_t e0, e1;
+  EBM_CUDA_TRY(cudaEventCreate(&e0));
+  EBM_CUDA_TRY(cudaEventCreate(&e1));
+  double best = 0.0, best_mhz = 0.0;
+  for (int rep = 0; rep < 5; ++rep) {
+    EBM_CUDA_TRY(cudaEventRecord(e0));
+    fp64_peak_kernel<<<blocks, threads>>>(out, iters, 1.0000001, 1e-9, cyc);
+    EBM_CUDA_TRY(cudaEventRecord(e1));
+    EBM_CUDA_TRY(cudaEventSynchronize(e1));
+    ebm_count_launch();
+    float ms = 0.f;
+    EBM_CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    const double flop = 2.0 * 8.0 * (double)iters * threads * (double)blocks;
+    const double tf = flop / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best) {
+      best = tf;
+      long long hc = 0;
+      EBM_CUDA_TRY(cudaMemcpy(&hc, cyc, sizeof(hc), cudaMemcpyDeviceToHost));
+      // blocks run in waves; a single block's cycle count vs its share of wall time gives the clock
+      const double waves = (double)blocks / (prop.multiProcessorCount * (2048 / threads));
+      best_mhz = (double)hc * (waves < 1.0 ? 1.0 : waves) / (ms * 1e-3) / 1e6;
+    }
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(out); cudaFree(cyc);
+  if (tflops) *tflops = best;
+  if (mhz) *mhz = best_mhz;
+  return EBM_OK;
+}

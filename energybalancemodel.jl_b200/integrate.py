@@ -1,0 +1,195 @@
+"""Host-side mirror of ``Infrastructure.integrate`` / ``step!`` on top of the C ABI.
+
+``integrate`` keeps the reference's signature (src/infrastructure.jl:615-618) and returns a
+``Solutions``; ``integrate_ensemble`` is the form the package extension adds -- vectors of
+``Forcing`` / parameter ``Collection`` / initial conditions, one entry per member.  Every
+numerical operation happens in libebm_cuda.so; there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _lib
+from .types import (CLASSIC_PAR_ORDER, CLASSIC_VARS, MIZ_PAR_ORDER, MIZ_VARS, Collection, Forcing, Solutions,
+                    SpaceTime)
+
+__all__ = ["integrate", "integrate_ensemble", "step", "EnsembleResult", "fp64_peak", "model_name"]
+
+_MIZ_STATE = ("Ei", "Ew", "h", "D", "phi")
+_CLASSIC_STATE = ("E", "Tg")
+
+
+def model_name(model) -> str:
+    """``:MIZ`` / ``:Classic``.  The reference dispatches on Val{:Classic}; ``:classic`` is a MethodError there."""
+    name = str(model).lstrip(":")
+    if name not in ("MIZ", "Classic"):
+        raise ValueError(f"no method matching step!(::Val{{:{name}}}, ...): model must be :MIZ or :Classic")
+    return name
+
+
+@dataclass
+class EnsembleResult:
+    """What one ensemble call returns (all NumPy, host memory)."""
+    model: str
+    spacetime: SpaceTime
+    nmem: int
+    field_stride: int
+    variables: tuple
+    diag: np.ndarray | None = None       # [nmem, dur, 3, 4]  (season: winter, summer, avg; mean T, mean E, ice area, ice edge)
+    seasonal: np.ndarray | None = None   # [nsel, dur, 3, nvar, nx]
+    raw: np.ndarray | None = None        # [nsel, nraw, nvar, nx]
+    final: dict = field(default_factory=dict)   # state arrays [nmem, nx]
+    flags: np.ndarray | None = None
+    newton_iters: np.ndarray | None = None
+    nonconv: np.ndarray | None = None
+
+    def solutions(self, k: int, forcing: Forcing, par: Collection, init: Collection, lastonly: bool) -> Solutions:
+        """Rebuild the reference's ``Solutions`` for the k-th member that has field output."""
+        sols = Solutions(self.spacetime, forcing, par, init, self.variables, lastonly)
+        for vi, v in enumerate(self.variables):
+            if self.raw is not None:
+                sols.raw[v][:] = self.raw[k, :, vi, :]
+            if self.seasonal is not None:
+                sols.seasonal.winter[v][:] = self.seasonal[k, :, 0, vi, :]
+                sols.seasonal.summer[v][:] = self.seasonal[k, :, 1, vi, :]
+                sols.seasonal.avg[v][:] = self.seasonal[k, :, 2, vi, :]
+        return sols
+
+
+def _rows(pars, order) -> np.ndarray:
+    out = np.empty((len(pars), len(order)))
+    for m, p in enumerate(pars):
+        try:
+            out[m] = [p[k] for k in order]
+        except KeyError as exc:   # Julia: KeyError from the Collection's Dict
+            raise KeyError(f"parameter {exc.args[0]!r} missing for member {m}") from exc
+    return out
+
+
+def _stack(inits, key, nx) -> np.ndarray:
+    a = np.ascontiguousarray(np.stack([np.asarray(i[key], dtype=np.float64) for i in inits]))
+    if a.shape != (len(inits), nx):
+        raise ValueError(f"init.{key} must have length nx={nx}")
+    return a
+
+
+def integrate_ensemble(model, st: SpaceTime, forcings, pars, inits, *, lastonly: bool = True, field_stride: int = 0,
+                       want_diag: bool = True, want_seasonal: bool | None = None, want_raw: bool | None = None,
+                       device: int = -1, strict: bool = False, years_per_launch: int = 0, debug=None,
+                       newton_tol: float = 0.0, newton_maxit: int = 0, T0guess=None) -> EnsembleResult:
+    """Integrate ``len(pars)`` independent members on one GPU.
+
+    ``field_stride`` > 0 selects the members (``m % field_stride == 0``) whose seasonal (L1) and raw (L2)
+    fields are returned; L0 diagnostics and final states are returned for every member.
+    """
+    name = model_name(model)
+    if debug is not None:
+        raise ValueError("`debug::Expr` cannot be evaluated on the device (EBM_ERR_UNSUPPORTED)")
+    nmem = len(pars)
+    if not (len(forcings) == nmem == len(inits)) or nmem == 0:
+        raise ValueError("forcings, pars and inits must be non-empty and of equal length")
+    lib = _lib.load()
+    nx, nt, dur = st.nx, st.nt, st.dur
+    grid = _lib.make_grid(st)
+    opt = _lib.make_options(device, lastonly, field_stride, strict, years_per_launch, newton_maxit, newton_tol)
+    forc = np.ascontiguousarray(np.stack([f.row() for f in forcings]))
+    nsel = (nmem + field_stride - 1) // field_stride if field_stride > 0 else 0
+    nraw = nt if lastonly else nt * dur
+    if want_seasonal is None:
+        want_seasonal = nsel > 0
+    if want_raw is None:
+        want_raw = nsel > 0
+    variables = CLASSIC_VARS if name == "Classic" else MIZ_VARS
+    nvar = len(variables)
+    res = EnsembleResult(name, st, nmem, field_stride, variables)
+    res.diag = np.empty((nmem, dur, 3, 4)) if want_diag else None
+    res.seasonal = np.empty((nsel, dur, 3, nvar, nx)) if (want_seasonal and nsel) else None
+    res.raw = np.empty((nsel, nraw, nvar, nx)) if (want_raw and nsel) else None
+    res.flags = np.zeros(nmem, dtype=np.int32)
+    flags_p = res.flags.ctypes.data_as(C.POINTER(C.c_int32))
+    if name == "Classic":
+        par = _rows(pars, CLASSIC_PAR_ORDER)
+        E0, Tg0 = _stack(inits, "E", nx), _stack(inits, "Tg", nx)
+        res.final = {"E": np.empty((nmem, nx)), "Tg": np.empty((nmem, nx))}
+        out = _lib.ClassicOutputs(_lib.dptr(res.diag), _lib.dptr(res.seasonal), _lib.dptr(res.raw),
+                                  _lib.dptr(res.final["E"]), _lib.dptr(res.final["Tg"]), flags_p)
+        _lib.check(lib.ebm_classic_run(C.byref(grid), nmem, _lib.dptr(par), _lib.dptr(forc), _lib.dptr(E0), _lib.dptr(Tg0),
+                                       C.byref(opt), C.byref(out)))
+    else:
+        par = _rows(pars, MIZ_PAR_ORDER)
+        init = [_stack(inits, k, nx) for k in _MIZ_STATE]
+        t0 = None if T0guess is None else np.ascontiguousarray(np.asarray(T0guess, dtype=np.float64).reshape(nmem, nx))
+        res.final = {k: np.empty((nmem, nx)) for k in _MIZ_STATE + ("T0",)}
+        res.newton_iters = np.zeros(nmem, dtype=np.int64)
+        res.nonconv = np.zeros(nmem, dtype=np.int64)
+        out = _lib.MizOutputs(_lib.dptr(res.diag), _lib.dptr(res.seasonal), _lib.dptr(res.raw),
+                              *[_lib.dptr(res.final[k]) for k in _MIZ_STATE + ("T0",)],
+                              res.newton_iters.ctypes.data_as(C.POINTER(C.c_int64)),
+                              res.nonconv.ctypes.data_as(C.POINTER(C.c_int64)), flags_p)
+        _lib.check(lib.ebm_miz_run(C.byref(grid), nmem, _lib.dptr(par), _lib.dptr(forc), *[_lib.dptr(a) for a in init],
+                                   _lib.dptr(t0), C.byref(opt), C.byref(out)))
+    return res
+
+
+def integrate(model, st: SpaceTime, forcing: Forcing, par: Collection, init: Collection, *, lastonly: bool = True,
+              debug=None, verbose: bool = False, device: int = -1, strict: bool = False) -> Solutions:
+    """``integrate(model, st, forcing, par, init; lastonly, debug, verbose) -> Solutions`` (one member).
+
+    Same arguments as src/infrastructure.jl:615-618.  ``verbose`` prints the closure's non-convergence count
+    (the reference @warns per step, src/miz.jl:61-63).
+    """
+    res = integrate_ensemble(model, st, [forcing], [par], [init], lastonly=lastonly, field_stride=1, want_diag=False,
+                             device=device, strict=strict, debug=debug)
+    if verbose and res.nonconv is not None and res.nonconv[0] > 0:
+        print(f"Warning: solving for T0 failed at {int(res.nonconv[0])} time steps.")
+    sols = res.solutions(0, forcing, par, init, lastonly)
+    sols.final = {k: v[0] for k, v in res.final.items()}
+    return sols
+
+
+def step(model, t: float, f: float, vars: Collection, st: SpaceTime, par: Collection) -> Collection:
+    """``step!(Val(model), t, f, vars, st, par)``: one time step of one member, in place, on the GPU.
+
+    For ``:MIZ`` the closure's warm start (the reference's persistent ``T0``, src/miz.jl:47) is carried
+    in ``vars.T0`` (zeros if absent).
+    """
+    name = model_name(model)
+    lib = _lib.load()
+    grid = _lib.make_grid(st)
+    # time index exactly as src/classic.jl:45
+    v = (t + st.dt / 2.0) * st.nt
+    r = v % st.nt
+    ti = int(round(st.nt if r == 0 else r))
+    nx = st.nx
+    if name == "Classic":
+        p = _rows([par], CLASSIC_PAR_ORDER)[0]
+        E = np.array(vars["E"], dtype=np.float64)
+        Tg = np.array(vars["Tg"], dtype=np.float64)
+        T, h = np.empty(nx), np.empty(nx)
+        _lib.check(lib.ebm_classic_step(C.byref(grid), _lib.dptr(p), ti, float(f), _lib.dptr(E), _lib.dptr(Tg),
+                                        _lib.dptr(T), _lib.dptr(h)))
+        vars["E"], vars["Tg"], vars["T"], vars["h"] = E, Tg, T, h
+    else:
+        p = _rows([par], MIZ_PAR_ORDER)[0]
+        stt = [np.array(vars[k], dtype=np.float64) for k in _MIZ_STATE]
+        T0 = np.array(vars["T0"], dtype=np.float64) if "T0" in vars else np.zeros(nx)
+        out = np.empty((len(MIZ_VARS), nx))
+        iters = C.c_int32(0)
+        _lib.check(lib.ebm_miz_step(C.byref(grid), _lib.dptr(p), ti, float(f), *[_lib.dptr(a) for a in stt],
+                                    _lib.dptr(T0), _lib.dptr(out), C.byref(iters)))
+        for vi, k in enumerate(MIZ_VARS):
+            vars[k] = out[vi].copy()
+        vars["T0"] = T0
+        vars["newton_iters"] = iters.value
+    return vars
+
+
+def fp64_peak(device: int = -1):
+    """Measured DFMA throughput (TFLOP/s, FMA = 2) and the SM clock estimate of the device."""
+    lib = _lib.load()
+    tf, mhz = C.c_double(0.0), C.c_double(0.0)
+    _lib.check(lib.ebm_fp64_peak(device, C.byref(tf), C.byref(mhz)))
+    return tf.value, mhz.value

@@ -1,0 +1,63 @@
+"""Shared helpers for the parity tests (tests only)."""
+from __future__ import annotations
+
+import numpy as np
+
+import ebm_b200 as ebm
+import oracle
+
+
+def classic_rows(pars):
+    return np.array([[p[k] for k in ebm.CLASSIC_PAR_ORDER] for p in pars])
+
+
+def miz_rows(pars):
+    return np.array([[p[k] for k in ebm.MIZ_PAR_ORDER] for p in pars])
+
+
+def forcing_rows(forcings):
+    return np.stack([f.row() for f in forcings])
+
+
+def warm_init(nx):
+    """WE15-style warm start (our choice): Tg = 10, E = cw*10."""
+    return ebm.Collection(E=np.full(nx, 98.0), Tg=np.full(nx, 10.0))
+
+
+def cold_init(nx):
+    return ebm.Collection(E=np.full(nx, -9.5), Tg=np.full(nx, -10.0))
+
+
+def oracle_classic(st, forcings, pars, inits, *, lastonly=True, raw=False, seasonal=False, solver=0, nthreads=0):
+    E0 = np.stack([np.asarray(i["E"], float) for i in inits])
+    Tg0 = np.stack([np.asarray(i["Tg"], float) for i in inits])
+    return oracle.classic_run(st.x, st.t, st.dur, st.winter.inx, st.summer.inx, classic_rows(pars),
+                              forcing_rows(forcings), E0, Tg0, solver=solver, lastonly=lastonly, want_raw=raw,
+                              want_seasonal=seasonal, nthreads=nthreads)
+
+
+def oracle_miz(st, forcings, pars, inits, *, T0=None, lastonly=True, raw=False, seasonal=False, nthreads=0, tol=1e-8):
+    arrs = [np.stack([np.asarray(i[k], float) for i in inits]) for k in ("Ei", "Ew", "h", "D", "phi")]
+    return oracle.miz_run(st.x, st.t, st.dur, st.winter.inx, st.summer.inx, st.grid_kind, miz_rows(pars),
+                          forcing_rows(forcings), *arrs, T0, newton_tol=tol, lastonly=lastonly, want_raw=raw,
+                          want_seasonal=seasonal, nthreads=nthreads)
+
+
+def rel_err(a, ref):
+    """|a - ref| / max(|ref|, 1) with NaN -> 0 on both sides (test/runtests.jl:42-43)."""
+    a0, r0 = np.nan_to_num(a, nan=0.0), np.nan_to_num(ref, nan=0.0)
+    return np.abs(a0 - r0) / np.maximum(np.abs(r0), 1.0)
+
+
+def oracle_diag_classic(seasonal, x):
+    """[nmem, dur, 3, 3, nx] oracle seasonal fields -> [nmem, dur, 3, 4] L0 diagnostics."""
+    nmem, dur = seasonal.shape[:2]
+    out = np.full((nmem, dur, 3, 4), np.nan)
+    for m in range(nmem):
+        for y in range(dur):
+            for s in range(3):
+                E, T = seasonal[m, y, s, 0], seasonal[m, y, s, 1]
+                if np.isnan(E).all():
+                    continue
+                out[m, y, s] = oracle.diag(T, E, None, x)
+    return out

@@ -1,0 +1,148 @@
+"""GPU parity tests for the classic path: libebm_cuda (through the C ABI / host mirror) vs the CPU oracle.
+
+Tolerance (BASELINE.json north_star): |gpu - ref| <= 1e-9 * max(|ref|, 1) at every compared
+sample for the fast kernel; the strict kernel and the one-step entry point must be bit-identical to the
+oracle (same operation order, same cos table, IEEE division, no FMA contraction).
+"""
+import numpy as np
+import pytest
+
+import ebm_b200 as ebm
+from helpers import (cold_init, forcing_rows, oracle_classic, oracle_diag_classic, rel_err, warm_init)
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+
+
+def _par(**kw):
+    p = ebm.default_parameters("Classic")
+    p.update(kw)
+    return p
+
+
+def test_single_step_bitwise():
+    """step!(Val(:Classic), ...) one step: bit-identical to the oracle, warm and cold states."""
+    st = ebm.SpaceTime(100, 2000, 1)
+    par = _par()
+    for init, f in ((warm_init(100), 0.0), (cold_init(100), 3.5)):
+        o = oracle_classic(ebm.SpaceTime(100, 2000, 1), [ebm.Forcing(f)], [par], [init], lastonly=False, raw=True)
+        v = ebm.Collection(E=init.E.copy(), Tg=init.Tg.copy())
+        ebm.step("Classic", st.t[0], f, v, st, par)
+        assert np.array_equal(v.E, o["raw"][0, 0, 0])
+        assert np.array_equal(v.T, o["raw"][0, 0, 1])
+        assert np.array_equal(v.h, o["raw"][0, 0, 2])
+
+
+def test_strict_kernel_bitwise_one_year():
+    """C1a with the literal-arithmetic kernel: every step of E, T, h and the final Tg bit-identical."""
+    st = ebm.SpaceTime(100, 2000, 1)
+    par, f, init = _par(), ebm.Forcing(0.0), warm_init(100)
+    o = oracle_classic(st, [f], [par], [init], lastonly=False, raw=True, seasonal=True)
+    r = ebm.integrate_ensemble("Classic", st, [f], [par], [init], lastonly=False, field_stride=1, strict=True)
+    assert np.array_equal(r.raw[0], o["raw"][0])
+    assert np.array_equal(r.final["Tg"], o["Tg"])
+    # winter / summer snapshots are copies of raw steps -> identical; annual mean differs only by summation order
+    assert np.array_equal(r.seasonal[0, :, :2], o["seasonal"][0, :, :2])
+    assert rel_err(r.seasonal[0, :, 2], o["seasonal"][0, :, 2]).max() < 1e-12
+
+
+def test_fast_kernel_one_year_every_step():
+    """C1a: classic 1-year, warm start, every step of E, T, h within 1e-9."""
+    st = ebm.SpaceTime(100, 2000, 1)
+    par, f, init = _par(), ebm.Forcing(0.0), warm_init(100)
+    o = oracle_classic(st, [f], [par], [init], lastonly=False, raw=True)
+    sols = ebm.integrate("Classic", st, f, par, init, lastonly=False)
+    for vi, v in enumerate(("E", "T", "h")):
+        err = rel_err(sols.raw[v], o["raw"][0, :, vi])
+        assert err.max() < TOL, (v, err.max(), np.unravel_index(err.argmax(), err.shape))
+    assert rel_err(sols.final["Tg"], o["Tg"][0]).max() < TOL
+    assert len(sols.ts) == 2000 and abs(sols.ts[0] - 0.00025) < 1e-15
+
+
+def test_fast_kernel_thirty_years_lastonly():
+    """C2: 30-year spin-up, lastonly: last-year raw, all seasonal fields, final state."""
+    st = ebm.SpaceTime(100, 2000, 30)
+    par, f, init = _par(), ebm.Forcing(0.0), warm_init(100)
+    o = oracle_classic(st, [f], [par], [init], lastonly=True, raw=True, seasonal=True)
+    sols = ebm.integrate("Classic", st, f, par, init)
+    for vi, v in enumerate(("E", "T", "h")):
+        assert rel_err(sols.raw[v], o["raw"][0, :, vi]).max() < TOL, v
+        for si, season in enumerate(("winter", "summer", "avg")):
+            assert rel_err(sols.seasonal[season][v], o["seasonal"][0, :, si, vi]).max() < TOL, (v, season)
+    assert abs(sols.ts[0] - 29.00025) < 1e-12
+    # WE15-like climate at year 30 (SURVEY Appendix D probe)
+    hm = ebm.hemispheric_mean(sols.seasonal.avg.T[29], st.x)
+    assert 16.9 < hm < 17.1
+
+
+def _ensemble(nmem, nx):
+    forcings, pars, inits = [], [], []
+    for m in range(nmem):
+        F = -20.0 + 40.0 * (m // 2) / max(nmem // 2 - 1, 1)
+        forcings.append(ebm.Forcing(F))
+        pars.append(_par(D=0.45 + 0.3 * (m % 7) / 6.0, B=1.9 + 0.05 * (m % 5)))
+        inits.append(warm_init(nx) if m % 2 == 0 else cold_init(nx))
+    return forcings, pars, inits
+
+
+@pytest.mark.parametrize("nmem,nx,nt", [(70, 100, 2000), (33, 60, 1000), (5, 37, 500), (40, 180, 2000)])
+def test_ensemble_diag_fields_and_state(nmem, nx, nt):
+    """Ragged member counts / other grids: L0 diagnostics, L1/L2 fields of strided members, final state."""
+    st = ebm.SpaceTime(nx, nt, 3)
+    forcings, pars, inits = _ensemble(nmem, nx)
+    o = oracle_classic(st, forcings, pars, inits, lastonly=True, raw=True, seasonal=True)
+    r = ebm.integrate_ensemble("Classic", st, forcings, pars, inits, field_stride=3)
+    assert r.flags.max() == 0
+    assert rel_err(r.final["E"], o["E"]).max() < TOL
+    assert rel_err(r.final["Tg"], o["Tg"]).max() < TOL
+    sel = np.arange(0, nmem, 3)
+    assert rel_err(r.raw, o["raw"][sel]).max() < TOL
+    assert rel_err(r.seasonal, o["seasonal"][sel]).max() < TOL
+    od = oracle_diag_classic(o["seasonal"], st.x)
+    d = rel_err(r.diag[..., :2], od[..., :2])
+    assert d.max() < TOL
+    # ice area / edge are step functions of the sign of E: equal unless a cell sits within 1e-9 of zero
+    near0 = (np.abs(o["seasonal"][:, :, :, 0, :]) < 1e-9).any(axis=-1)
+    mism = (np.abs(r.diag[..., 2:] - od[..., 2:]) > 1e-9).any(axis=-1)
+    assert not (mism & ~near0).any()
+
+
+def test_ramp_forcing_and_chained_launches():
+    """Forcing{false} evaluated per step on the device; splitting the run into launches changes nothing."""
+    st = ebm.SpaceTime(100, 2000, 6)
+    forcings = [ebm.Forcing(0.0, 4.0, -2.0, (1, 1), (2.0, -3.0)), ebm.Forcing(-1.0, 1.0, -1.0, (0, 2), (1.0, -1.0)),
+                ebm.Forcing(2.5)]
+    pars = [_par()] * 3
+    inits = [warm_init(100), cold_init(100), warm_init(100)]
+    o = oracle_classic(st, forcings, pars, inits, seasonal=True)
+    a = ebm.integrate_ensemble("Classic", st, forcings, pars, inits, field_stride=1, want_raw=False)
+    b = ebm.integrate_ensemble("Classic", st, forcings, pars, inits, field_stride=1, want_raw=False, years_per_launch=2)
+    assert rel_err(a.seasonal, o["seasonal"]).max() < TOL
+    assert np.array_equal(a.final["E"], b.final["E"]) and np.array_equal(a.final["Tg"], b.final["Tg"])
+    assert np.array_equal(np.nan_to_num(a.seasonal), np.nan_to_num(b.seasonal))
+    assert np.array_equal(a.diag, b.diag)
+
+
+def test_energy_budget_and_thickness_invariants():
+    """Size-independent properties on a 2048-member ensemble: h = -E/Lf*(E<0) >= 0, T = E/cw where E >= 0,
+    finite state, and the two hysteresis branches are both populated."""
+    nmem, nx = 2048, 100
+    st = ebm.SpaceTime(nx, 2000, 2)
+    par = _par()
+    forcings = [ebm.Forcing(-20.0 + 40.0 * (m % 1024) / 1023.0) for m in range(nmem)]
+    inits = [warm_init(nx) if m < 1024 else cold_init(nx) for m in range(nmem)]
+    r = ebm.integrate_ensemble("Classic", st, forcings, [par] * nmem, inits, field_stride=64)
+    assert r.flags.max() == 0 and np.isfinite(r.final["E"]).all() and np.isfinite(r.final["Tg"]).all()
+    E, T, h = r.raw[:, :, 0], r.raw[:, :, 1], r.raw[:, :, 2]
+    assert (h >= 0).all()
+    assert np.allclose(h, np.where(E < 0, -E / par.Lf, 0.0), rtol=1e-14, atol=0)
+    # T of step i is computed from E BEFORE that step's Euler update (classic.jl:51 precedes :53)
+    Ep, Tn = E[:, :-1], T[:, 1:]
+    assert np.allclose(Tn[Ep >= 0], Ep[Ep >= 0] / par.cw, rtol=1e-13, atol=0)
+    assert (Tn[Ep < 0] <= 0).all()
+    area = r.diag[:, -1, 2, 2]
+    assert area[:1024].min() < 0.5 and area[1024:].max() > 5.0   # warm branch ice-free, cold branch snowball
+    # spot-check 8 members against the oracle
+    idx = list(range(0, nmem, 256))
+    o = oracle_classic(st, [forcings[i] for i in idx], [par] * len(idx), [inits[i] for i in idx])
+    assert rel_err(r.final["E"][idx], o["E"]).max() < TOL
