@@ -206,6 +206,7 @@ extern "C" int32_t ebm_classic_run_device(const ebm_grid_t* grid, const ebm_clas
   ebm_options_t opt = opt_in ? *opt_in : default_options();
   EBM_TRY(select_device(opt));
   if ((args->seasonal || args->raw) && opt.field_stride <= 0) { ebm_set_error("seasonal/raw output requested but field_stride == 0"); return EBM_ERR_INVALID; }
+  if (opt.step_limit > 0) { ebm_set_error("step_limit is only supported by the MIZ path"); return EBM_ERR_UNSUPPORTED; }
   ClassicKArgs a;
   memset(&a, 0, sizeof(a));
   EBM_TRY(get_tables(grid, &a.g, stream));
@@ -327,6 +328,7 @@ extern "C" int32_t ebm_miz_run_device(const ebm_grid_t* grid, const ebm_miz_devi
   a.lastonly = opt.lastonly; a.field_stride = opt.field_stride;
   a.maxit = opt.newton_maxit > 0 ? opt.newton_maxit : 100;
   a.tol = opt.newton_tol > 0.0 ? opt.newton_tol : 1e-8;
+  a.step_limit = opt.step_limit > 0 ? opt.step_limit : 0;
   a.par = args->par; a.forc = args->forc;
   a.Ei = args->Ei; a.Ew = args->Ew; a.h = args->h; a.D = args->D; a.phi = args->phi; a.T0 = args->T0;
   a.diag = args->diag; a.seasonal = args->seasonal; a.raw = args->raw;
@@ -413,17 +415,20 @@ extern "C" int32_t ebm_miz_step(const ebm_grid_t* grid, const ebm_miz_params_t* 
   EbmGridTables tabs;
   EBM_TRY(get_tables(grid, &tabs, 0));
   DevBufs B;
-  double* d = nullptr; int* dit = nullptr;
+  double* d = nullptr; long long* dit = nullptr;
   EBM_TRY(B.alloc(&d, (size_t)EBM_MIZ_NPAR + (6 + EBM_MIZ_NVAR) * (size_t)nx));
   EBM_TRY(B.alloc(&dit, 1));
   double* dpar = d; double* st6 = d + EBM_MIZ_NPAR; double* dvars = st6 + 6 * nx;
   double* host6[6] = {Ei, Ew, h, D, phi, T0};
   EBM_CUDA_TRY(cudaMemcpy(dpar, par, sizeof(double) * EBM_MIZ_NPAR, cudaMemcpyHostToDevice));
   for (int q = 0; q < 6; ++q) EBM_CUDA_TRY(cudaMemcpy(st6 + q * nx, host6[q], sizeof(double) * nx, cudaMemcpyHostToDevice));
+  EBM_CUDA_TRY(cudaMemset(dit, 0, sizeof(long long)));
   EBM_TRY(ebm_launch_miz_single_step(tabs, dpar, ti, f, 1e-8, 100, st6, st6 + nx, st6 + 2 * nx, st6 + 3 * nx, st6 + 4 * nx,
                                      st6 + 5 * nx, dvars, dit, 0));
   for (int q = 0; q < 6; ++q) EBM_CUDA_TRY(cudaMemcpy(host6[q], st6 + q * nx, sizeof(double) * nx, cudaMemcpyDeviceToHost));
   EBM_CUDA_TRY(cudaMemcpy(vars_out, dvars, sizeof(double) * EBM_MIZ_NVAR * nx, cudaMemcpyDeviceToHost));
-  if (newton_iters) EBM_CUDA_TRY(cudaMemcpy(newton_iters, dit, sizeof(int), cudaMemcpyDeviceToHost));
+  long long hit = 0;
+  EBM_CUDA_TRY(cudaMemcpy(&hit, dit, sizeof(long long), cudaMemcpyDeviceToHost));
+  if (newton_iters) *newton_iters = (int32_t)hit;
   return EBM_OK;
 }

@@ -57,6 +57,8 @@ struct MizKArgs {
   int year0, nyears;
   int winter_inx, summer_inx, lastonly, field_stride, all_const_forcing;
   int maxit; double tol;
+  int step_limit;                  // > 0: stop after this many steps of the run (partial last year)
+  int single_ti; double single_f;  // > 0: exactly one step at year-index single_ti with forcing single_f (ebm_miz_step)
   EbmGridTables g;
   const double* par;             // [22][nmem]
   const double* forc;            // [10][nmem]
@@ -73,9 +75,11 @@ int ebm_launch_classic_strict(const ClassicKArgs& a, cudaStream_t stream);
 int ebm_launch_classic_single_step(const EbmGridTables& g, const double* par15, int ti, double f,
                                    double* E, double* Tg, double* T, double* h, cudaStream_t stream);
 int ebm_launch_miz(const MizKArgs& a, int strict, cudaStream_t stream);
+int ebm_launch_miz_fast(const MizKArgs& a, cudaStream_t stream);     // miz_kernel.cu
+int ebm_launch_miz_strict(const MizKArgs& a, cudaStream_t stream);   // miz_strict.cu (-fmad=false)
 int ebm_launch_miz_single_step(const EbmGridTables& g, const double* par22, int ti, double f, double tol, int maxit,
                                double* Ei, double* Ew, double* h, double* D, double* phi, double* T0,
-                               double* vars_out, int* iters, cudaStream_t stream);
+                               double* vars_out, long long* iters, cudaStream_t stream);
 int ebm_launch_transpose(const double* src, double* dst, long long rows, long long cols, cudaStream_t stream);
 int ebm_launch_fill(double* dst, long long n, double v, cudaStream_t stream);
 int ebm_run_fp64_peak(int device, double* tflops, double* mhz);

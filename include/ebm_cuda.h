@@ -89,7 +89,12 @@ typedef struct ebm_options {
                                tridiagonal solve) -- slow, for parity debugging */
   int32_t years_per_launch; /* 0: whole run in one launch */
   int32_t newton_maxit;     /* MIZ closure iteration cap, 0 -> 100 */
-  double newton_tol;        /* MIZ closure max|residual| stop, 0 -> 1e-8 (miz.jl:137 abstol) */
+  double newton_tol;        /* MIZ closure max|residual| stop, 0 -> 1e-8 (miz.jl:59 abstol) */
+  int32_t step_limit;       /* MIZ only, > 0: stop after this many time steps (partial last year; outputs of the
+                               steps not taken stay NaN).  Used to compare short horizons from a given state: the
+                               MIZ dynamics amplify rounding differences, so long-run pointwise
+                               parity is not defined even for the reference itself. */
+  int32_t reserved;
 } ebm_options_t;
 
 /* ---- outputs (host entry points).  Any pointer may be NULL = not wanted. ------------------------

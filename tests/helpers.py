@@ -61,3 +61,32 @@ def oracle_diag_classic(seasonal, x):
                     continue
                 out[m, y, s] = oracle.diag(T, E, None, x)
     return out
+
+
+def oracle_diag_miz(seasonal, x):
+    """[nmem, dur, 3, 10, nx] oracle seasonal fields -> [nmem, dur, 3, 4] L0 diagnostics (ice area from phi)."""
+    iT, iE, iP = ebm.MIZ_VARS.index("T"), ebm.MIZ_VARS.index("E"), ebm.MIZ_VARS.index("phi")
+    nmem, dur = seasonal.shape[:2]
+    out = np.full((nmem, dur, 3, 4), np.nan)
+    for m in range(nmem):
+        for y in range(dur):
+            for s in range(3):
+                out[m, y, s] = oracle.diag(seasonal[m, y, s, iT], seasonal[m, y, s, iE], seasonal[m, y, s, iP], x)
+    return out
+
+
+def assert_close(a, ref, tol, what="", flag=None, flag_tol=1e-6, max_flag_frac=1e-3):
+    """max |a - ref| / max(|ref|, 1) < tol with a short failure message.  `flag` (bool array, same shape) marks
+    branch-threshold samples (SURVEY 8c "flagged cells"): they are counted, must stay under `flag_tol`, and must be
+    rare; every other sample must meet `tol`."""
+    err = rel_err(a, ref)
+    if flag is None:
+        flag = np.zeros(err.shape, dtype=bool)
+    assert flag.mean() <= max_flag_frac, f"{what}: {flag.sum()} flagged samples of {flag.size}"
+    e = np.where(flag, 0.0, err)
+    if e.max() >= tol:
+        i = np.unravel_index(e.argmax(), e.shape)
+        raise AssertionError(f"{what}: err {e.max():.3e} >= {tol:.1e} at {i}: got {a[i]!r}, ref {ref[i]!r}")
+    if flag.any() and err[flag].max() >= flag_tol:
+        raise AssertionError(f"{what}: flagged-cell err {err[flag].max():.3e} >= {flag_tol:.1e}")
+    return int(flag.sum())

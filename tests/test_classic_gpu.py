@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 import ebm_b200 as ebm
-from helpers import (cold_init, forcing_rows, oracle_classic, oracle_diag_classic, rel_err, warm_init)
+from helpers import (assert_close, cold_init, forcing_rows, oracle_classic, oracle_diag_classic, rel_err, warm_init)
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-9
@@ -93,14 +93,13 @@ def test_ensemble_diag_fields_and_state(nmem, nx, nt):
     o = oracle_classic(st, forcings, pars, inits, lastonly=True, raw=True, seasonal=True)
     r = ebm.integrate_ensemble("Classic", st, forcings, pars, inits, field_stride=3)
     assert r.flags.max() == 0
-    assert rel_err(r.final["E"], o["E"]).max() < TOL
-    assert rel_err(r.final["Tg"], o["Tg"]).max() < TOL
+    assert_close(r.final["E"], o["E"], TOL, "final E")
+    assert_close(r.final["Tg"], o["Tg"], TOL, "final Tg")
     sel = np.arange(0, nmem, 3)
-    assert rel_err(r.raw, o["raw"][sel]).max() < TOL
-    assert rel_err(r.seasonal, o["seasonal"][sel]).max() < TOL
+    assert_close(r.raw, o["raw"][sel], TOL, "raw")
+    assert_close(r.seasonal, o["seasonal"][sel], TOL, "seasonal")
     od = oracle_diag_classic(o["seasonal"], st.x)
-    d = rel_err(r.diag[..., :2], od[..., :2])
-    assert d.max() < TOL
+    assert_close(r.diag[..., :2], od[..., :2], TOL, "diag")
     # ice area / edge are step functions of the sign of E: equal unless a cell sits within 1e-9 of zero
     near0 = (np.abs(o["seasonal"][:, :, :, 0, :]) < 1e-9).any(axis=-1)
     mism = (np.abs(r.diag[..., 2:] - od[..., 2:]) > 1e-9).any(axis=-1)

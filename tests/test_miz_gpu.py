@@ -1,0 +1,262 @@
+"""GPU parity tests for the MIZ path: libebm_cuda (through the C ABI / host mirror) vs the CPU oracle.
+
+The MIZ model amplifies rounding-level differences: perturbing the reference algorithm's initial state by 1e-13
+changes every variable by O(0.1) within 200 steps of the spin-up and the year-30 climate by ~2e-3 (measured
+with the oracle, DESIGN.md "MIZ sensitivity").  Long-run pointwise parity is therefore undefined even between
+two runs of the reference on different libm/BLAS builds -- which is why the reference's own test compares step
+10 only (test/runtests.jl:37-47).  Parity is established in layers:
+
+  1. the strict kernel (literal operation order, -fmad=false, serial Thomas) and the one-step entry point are
+     BIT-IDENTICAL to the oracle over whole trajectories (1 and 30 years, both grid kinds, ensembles);
+  2. the fast kernel (same source, FMA contraction + warp-parallel solve) meets the reference's criterion
+     (step 10, rtol = sqrt(eps)) and stays within that tolerance over short horizons (20 steps) started from
+     oracle states taken all along a 30-year trajectory and across a parameter ensemble;
+  3. long fast runs are checked through determinism (chained launches / restarts are bitwise reproducible),
+     sampler self-consistency, state invariants and climatology within the model's own sensitivity envelope.
+
+Tolerance: rtol = sqrt(eps) = 1.49e-8 (Julia isapprox default) with an absolute floor of the same size
+(|ref| < 1 compared absolutely), NaN masks compared separately.
+"""
+import numpy as np
+import pytest
+
+import ebm_b200 as ebm
+from helpers import oracle_diag_miz, oracle_miz, rel_err
+
+pytestmark = pytest.mark.gpu
+RTOL = 1.4901161193847656e-08   # sqrt(eps(Float64)): Julia's isapprox default
+STATE = ("Ei", "Ew", "h", "D", "phi")
+
+
+def _par(**kw):
+    p = ebm.default_parameters("MIZ")
+    p.update(kw)
+    return p
+
+
+def _zero(nx):
+    z = np.zeros(nx)
+    return ebm.Collection(Ei=z.copy(), Ew=z.copy(), h=z.copy(), D=z.copy(), phi=z.copy())
+
+
+def _same(a, b):
+    """bit-for-bit, NaN == NaN"""
+    return np.array_equal(a, b, equal_nan=True)
+
+
+def _check(a, ref, what, tol=RTOL):
+    assert np.array_equal(np.isnan(a), np.isnan(ref)), f"{what}: NaN masks differ"
+    err = rel_err(a, ref)
+    assert err.max() < tol, (what, err.max(), np.unravel_index(err.argmax(), err.shape))
+
+
+def test_fixture_setup_matches_reference_test_criterion():
+    """test/runtests.jl:20-48: MIZ, SpaceTime{sin}(180, 2000, 1), zero init, F = 0; raw[var][10] of the ten
+    variables, NaN -> 0, element-wise isapprox(rtol = sqrt(eps), atol = 0)."""
+    st = ebm.SpaceTime(180, 2000, 1, "sin")
+    par, f, init = _par(), ebm.Forcing(0.0), _zero(180)
+    sols = ebm.integrate("MIZ", st, f, par, init)
+    o = oracle_miz(st, [f], [par], [init], raw=True)
+    for vi, v in enumerate(ebm.MIZ_VARS):
+        a, b = np.nan_to_num(sols.raw[v][9]), np.nan_to_num(o["raw"][0, 9, vi])
+        assert np.all(np.abs(a - b) <= RTOL * np.maximum(np.abs(a), np.abs(b))), v
+    # known-answer probe values of SURVEY Appendix D (step 10 of the fixture run)
+    assert abs(sols.raw.E[9][0] - 0.509) < 2e-3 and abs(sols.raw.E[9][-1] + 1.174) < 2e-3
+    assert abs(np.nan_to_num(sols.raw.Ti[9])[-1] + 11.24) < 2e-2
+
+
+def test_single_step_bitwise_chain():
+    """step!(Val(:MIZ), ...) for 12 consecutive steps from the zero state: every stored variable of every step
+    and the carried state are bit-identical to the oracle (NaN masks included)."""
+    st = ebm.SpaceTime(180, 2000, 1, "sin")
+    par, f = _par(), 0.75
+    o = oracle_miz(st, [ebm.Forcing(f)], [par], [_zero(180)], lastonly=False, raw=True)
+    v = _zero(180)
+    for k in range(12):
+        ebm.step("MIZ", st.t[k], f, v, st, par)
+        for vi, name in enumerate(ebm.MIZ_VARS):
+            assert _same(v[name], o["raw"][0, k, vi]), (k, name)
+    assert v["newton_iters"] >= 0
+
+
+@pytest.mark.parametrize("xfunc,nx", [("sin", 180), ("identity", 100)])
+def test_strict_kernel_bitwise_one_year(xfunc, nx):
+    """C1b with the literal-arithmetic kernel: all 2000 steps of the ten variables, the final state, the closure
+    warm start and the Newton iteration count are bit-identical to the oracle, on both grid kinds."""
+    st = ebm.SpaceTime(nx, 2000, 1, xfunc)
+    par, f, init = _par(), ebm.Forcing(0.0), _zero(nx)
+    o = oracle_miz(st, [f], [par], [init], lastonly=False, raw=True, seasonal=True)
+    r = ebm.integrate_ensemble("MIZ", st, [f], [par], [init], lastonly=False, field_stride=1, strict=True)
+    for vi, name in enumerate(ebm.MIZ_VARS):
+        assert _same(r.raw[0, :, vi], o["raw"][0, :, vi]), name
+    for k in STATE + ("T0",):
+        assert _same(r.final[k], o[k]), k
+    assert int(r.newton_iters[0]) == int(o["newton_iters"][0]) and int(r.nonconv[0]) == int(o["nonconv"][0])
+    assert _same(r.seasonal[0, :, :2], o["seasonal"][0, :, :2])      # winter / summer snapshots are copies
+    _check(r.seasonal[0, :, 2], o["seasonal"][0, :, 2], "annual mean", 1e-12)   # summation order only
+
+
+HORIZON = 20
+
+
+def test_fast_kernel_short_horizon_from_zero_state():
+    """C1b setup: the first 20 steps of all ten variables within the reference's tolerance."""
+    st = ebm.SpaceTime(180, 2000, 1, "sin")
+    par, f, init = _par(), ebm.Forcing(0.0), _zero(180)
+    o = oracle_miz(st, [f], [par], [init], lastonly=False, raw=True)
+    r = ebm.integrate_ensemble("MIZ", st, [f], [par], [init], lastonly=False, field_stride=1, step_limit=HORIZON)
+    for vi, v in enumerate(ebm.MIZ_VARS):
+        _check(r.raw[0, :HORIZON, vi], o["raw"][0, :HORIZON, vi], v)
+    assert np.isnan(r.raw[0, HORIZON:]).all()          # steps not taken stay NaN (undef in the reference)
+
+
+def test_fast_kernel_short_horizons_along_thirty_year_trajectory():
+    """C3 trajectory (docstring example, src/EnergyBalanceModel.jl:18-57): restart the fast kernel from the
+    oracle's state (incl. the closure warm start) after 1, 2, 3, 5, 10, 20 and 30 years; 20 steps each."""
+    par, f = _par(), ebm.Forcing(0.0)
+    inits, T0s = [], []
+    for years in (1, 2, 3, 5, 10, 20, 30):
+        o = oracle_miz(ebm.SpaceTime(180, 2000, years, "sin"), [f], [par], [_zero(180)])
+        inits.append(ebm.Collection({k: o[k][0] for k in STATE}))
+        T0s.append(o["T0"][0])
+    st = ebm.SpaceTime(180, 2000, 1, "sin")
+    n = len(inits)
+    o = oracle_miz(st, [f] * n, [par] * n, inits, T0=np.stack(T0s), lastonly=False, raw=True)
+    r = ebm.integrate_ensemble("MIZ", st, [f] * n, [par] * n, inits, T0guess=np.stack(T0s), lastonly=False,
+                               field_stride=1, step_limit=HORIZON)
+    for vi, v in enumerate(ebm.MIZ_VARS):
+        _check(r.raw[:, :HORIZON, vi], o["raw"][:, :HORIZON, vi], v)
+
+
+def test_strict_kernel_bitwise_thirty_years():
+    """C3 with the literal-arithmetic kernel: 30 years, last-year raw + all seasonal snapshots + final state
+    bit-identical to the oracle."""
+    st = ebm.SpaceTime(180, 2000, 30, "sin")
+    par, f, init = _par(), ebm.Forcing(0.0), _zero(180)
+    o = oracle_miz(st, [f], [par], [init], raw=True, seasonal=True)
+    r = ebm.integrate_ensemble("MIZ", st, [f], [par], [init], field_stride=1, strict=True)
+    assert _same(r.raw[0], o["raw"][0])
+    assert _same(r.seasonal[0, :, :2], o["seasonal"][0, :, :2])
+    for k in STATE + ("T0",):
+        assert _same(r.final[k], o[k]), k
+    assert int(r.newton_iters[0]) == int(o["newton_iters"][0])
+
+
+def test_fast_kernel_thirty_years_climatology():
+    """C3 with the fast kernel: Solutions layout, and the year-30 climate within the model's own sensitivity
+    envelope (a 1e-13 perturbation of the oracle moves these diagnostics by ~2e-3)."""
+    st = ebm.SpaceTime(180, 2000, 30, "sin")
+    par, f, init = _par(), ebm.Forcing(0.0), _zero(180)
+    o = oracle_miz(st, [f], [par], [init], seasonal=True)
+    r = ebm.integrate_ensemble("MIZ", st, [f], [par], [init], field_stride=1)
+    sols = r.solutions(0, f, par, init, True)
+    assert abs(sols.ts[0] - 29.00025) < 1e-12 and len(sols.ts) == 2000 and sols.raw.E.shape == (2000, 180)
+    od = oracle_diag_miz(o["seasonal"], st.x)
+    d = np.abs(r.diag[0, 29] - od[0, 29])
+    assert d[:, 0].max() < 0.05 and d[:, 1].max() < 0.1 and d[:, 2].max() < 0.02 and d[:, 3].max() < 0.03, d
+    ice_cells = int((sols.raw.phi[-1] > 0).sum())
+    assert 30 <= ice_cells <= 90                       # SURVEY Appendix D probe: ice cells 175 -> 57
+    assert r.nonconv[0] == 0 and r.flags[0] == 0
+
+
+def _ensemble(nmem):
+    forcings, pars = [], []
+    for m in range(nmem):
+        forcings.append(ebm.Forcing(-2.0 + 4.0 * (m % 5) / 4.0))
+        pars.append(_par(D=0.45 + 0.3 * (m % 7) / 6.0, B=1.8 + 0.1 * (m % 4), ai=0.35 + 0.02 * (m % 6),
+                         k=1.5 + 0.25 * (m % 5), m1=50.4576 * (0.5 + 0.25 * (m % 3))))
+    return forcings, pars
+
+
+@pytest.mark.parametrize("nmem,nx,nt,xfunc", [(37, 180, 2000, "sin"), (9, 100, 1000, "identity"),
+                                              (5, 50, 800, "sin"), (6, 250, 2000, "sin")])
+def test_ensemble_strict_bitwise_and_fast_short_horizon(nmem, nx, nt, xfunc):
+    """Ragged member counts, both grid kinds, other grid sizes, per-member parameters and forcing.
+    Strict kernel: final state of every member after 1 year bit-identical.  Fast kernel: first 20 steps of the
+    strided members' fields within tolerance."""
+    st = ebm.SpaceTime(nx, nt, 1, xfunc)
+    forcings, pars = _ensemble(nmem)
+    inits = [_zero(nx) for _ in range(nmem)]
+    o = oracle_miz(st, forcings, pars, inits, lastonly=False, raw=True)
+    rs = ebm.integrate_ensemble("MIZ", st, forcings, pars, inits, strict=True)
+    for k in STATE + ("T0",):
+        assert _same(rs.final[k], o[k]), k
+    assert np.array_equal(rs.newton_iters, o["newton_iters"])
+    r = ebm.integrate_ensemble("MIZ", st, forcings, pars, inits, lastonly=False, field_stride=4, step_limit=HORIZON)
+    sel = np.arange(0, nmem, 4)
+    _check(r.raw[:, :HORIZON], o["raw"][sel, :HORIZON], "raw")
+
+
+def test_sampler_self_consistency_and_diagnostics():
+    """savesol! semantics on the device (infrastructure.jl:549-591): winter / summer snapshots are the raw steps
+    winter.inx / summer.inx, the annual mean is the mean of the year's raw steps, and the L0 diagnostics equal
+    hemispheric_mean / ice area / ice edge of those very fields.  (Self-consistency: independent of the
+    trajectory's sensitivity.)"""
+    nx, nmem = 180, 10
+    st = ebm.SpaceTime(nx, 2000, 2, "sin")
+    forcings, pars = _ensemble(nmem)
+    r = ebm.integrate_ensemble("MIZ", st, forcings, pars, [_zero(nx)] * nmem, lastonly=False, field_stride=3)
+    nsel = len(range(0, nmem, 3))
+    assert r.raw.shape == (nsel, 4000, 10, nx) and r.seasonal.shape == (nsel, 2, 3, 10, nx)
+    for y in range(2):
+        assert _same(r.seasonal[:, y, 0], r.raw[:, y * 2000 + st.winter.inx - 1])
+        assert _same(r.seasonal[:, y, 1], r.raw[:, y * 2000 + st.summer.inx - 1])
+        mean = r.raw[:, y * 2000:(y + 1) * 2000].mean(axis=1)
+        _check(r.seasonal[:, y, 2], mean, "annual mean", 1e-11)
+    d = oracle_diag_miz(r.seasonal, st.x)
+    sel = np.arange(0, nmem, 3)
+    _check(r.diag[sel][..., :3], d[..., :3], "diag", 1e-11)
+    assert np.abs(r.diag[sel][..., 3] - d[..., 3]).max() == 0.0
+
+
+def test_ramp_forcing_and_chained_launches():
+    """Forcing{false} per step on the device (strict run bit-identical to the oracle); splitting a fast run into
+    launches (state + warm start carried through HBM) changes nothing."""
+    st = ebm.SpaceTime(180, 2000, 3, "sin")
+    forcings = [ebm.Forcing(0.0, 4.0, -2.0, (1, 0), (4.0, -6.0)), ebm.Forcing(1.5), ebm.Forcing(-1.0, 1.0, -1.0, (0, 1), (2.0, -2.0))]
+    pars = [_par()] * 3
+    inits = [_zero(180) for _ in range(3)]
+    o = oracle_miz(st, forcings, pars, inits)
+    s = ebm.integrate_ensemble("MIZ", st, forcings, pars, inits, strict=True)
+    for k in STATE:
+        assert _same(s.final[k], o[k]), k
+    a = ebm.integrate_ensemble("MIZ", st, forcings, pars, inits, field_stride=1, want_raw=False)
+    b = ebm.integrate_ensemble("MIZ", st, forcings, pars, inits, field_stride=1, want_raw=False, years_per_launch=1)
+    for k in STATE + ("T0",):
+        assert _same(a.final[k], b.final[k]), k
+    assert _same(a.seasonal, b.seasonal) and _same(a.diag, b.diag)
+    assert np.array_equal(a.newton_iters, b.newton_iters)
+
+
+def test_restart_from_final_state_reproduces_long_run():
+    """Checkpoint/restart: a 2-year run == two 1-year runs chained through the returned state and
+    the returned closure warm start T0 (the reference's persistent T0, src/miz.jl:47,64)."""
+    par, f = _par(), ebm.Forcing(0.5)
+    full = ebm.integrate_ensemble("MIZ", ebm.SpaceTime(180, 2000, 2, "sin"), [f], [par], [_zero(180)])
+    st1 = ebm.SpaceTime(180, 2000, 1, "sin")
+    a = ebm.integrate_ensemble("MIZ", st1, [f], [par], [_zero(180)])
+    init2 = ebm.Collection({k: a.final[k][0] for k in STATE})
+    b = ebm.integrate_ensemble("MIZ", st1, [f], [par], [init2], T0guess=a.final["T0"])
+    for k in STATE + ("T0",):
+        assert _same(full.final[k], b.final[k]), k
+
+
+def test_state_invariants_large_ensemble():
+    """Size-independent properties on a 4096-member parameter sweep: phi in [0,1], h >= 0, D in {0} U [Dmin,Dmax],
+    Ei <= 0 <= Ew, finite state, closure converged everywhere; year-1 climate of spot-checked members within
+    the sensitivity envelope of the oracle."""
+    nmem, nx = 4096, 180
+    st = ebm.SpaceTime(nx, 2000, 1, "sin")
+    forcings, pars = _ensemble(nmem)
+    r = ebm.integrate_ensemble("MIZ", st, forcings, pars, [_zero(nx)] * nmem)
+    assert r.flags.max() == 0 and r.nonconv.max() == 0
+    f = r.final
+    assert (f["phi"] >= 0).all() and (f["phi"] <= 1).all() and (f["h"] >= 0).all()
+    assert (f["Ei"] <= 0).all() and (f["Ew"] >= 0).all()
+    D = f["D"]
+    assert (((D == 0) | ((D >= 1.0) & (D <= 156.0)))).all()
+    assert np.isfinite(r.diag).all()
+    idx = list(range(0, nmem, 512))
+    o = oracle_miz(st, [forcings[i] for i in idx], [pars[i] for i in idx], [_zero(nx)] * len(idx), seasonal=True)
+    od = oracle_diag_miz(o["seasonal"], st.x)
+    assert np.abs(r.diag[idx, 0, 2, 0] - od[:, 0, 2, 0]).max() < 0.5      # annual-mean hemispheric T
