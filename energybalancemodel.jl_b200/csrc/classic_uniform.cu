@@ -481,10 +481,10 @@ int ebm_launch_classic_uniform(const ClassicKArgs& a, int variant, cudaStream_t 
   if (a.nx > ebm_classic_uniform_max_nx()) return EBM_OK;   // larger grids: the general kernel integrates every group
   switch (variant) {
     // <K cells/thread, WB bands, MW members/CTA, max registers/thread>
-    case 1: return launch_uniform<13, 8, 16, 255>(a, stream);   // 2 warps / sub-partition: 2 CTAs per SM
+    case 1: return launch_uniform<13, 8, 16, 168>(a, stream);   // 3 warps / sub-partition: 3 CTAs per SM
     case 2: return launch_uniform<13, 8, 16, 128>(a, stream);   // 4 warps / sub-partition: 4 CTAs per SM (spills)
     case 3: return launch_uniform<7, 16, 16, 128>(a, stream);   // 8 warps per CTA, 2 CTAs per SM
     case 4: return launch_uniform<7, 16, 16, 96>(a, stream);
-    default: return launch_uniform<13, 8, 16, 168>(a, stream);  // 3 warps / sub-partition: 3 CTAs per SM
+    default: return launch_uniform<13, 8, 16, 255>(a, stream);  // 2 warps / sub-partition: 2 CTAs per SM, no spills (fastest measured)
   }
 }

@@ -1,7 +1,492 @@
-// miz_kernel.cu -- fast flavour of the MIZ ensemble kernel (see miz_kernel.cuh) and the launch dispatch.
-#include "miz_kernel.cuh"
+// miz_kernel.cu -- production (fast) flavour of the marginal-ice-zone (MIZ) ensemble step kernel, and the launch dispatch.
+//
+// Replaces, for a whole ensemble and many years per launch, the reference's
+//   integrate loop            src/infrastructure.jl:630-634
+//   step!(::Val{:MIZ})        src/miz.jl:150-196        (arithmetic spec: SURVEY.md Appendix B)
+//   solveTi / T0eq            src/miz.jl:33-68          (closure: semi-smooth Newton, tridiagonal Jacobian)
+//   diffusion!                src/infrastructure.jl:495-527 (identity grid and generic flux-form stencil)
+//   savesol! / annual_mean    src/infrastructure.jl:536-591
+// The literal-order twin of this kernel (bit-identical to the oracle) is miz_literal.cuh / miz_strict.cu; the
+// algebra here is the same step with
+//   * every division turned into a reciprocal (MUFU.RCP64H seed + 2 Newton steps) times a product, reciprocals
+//     shared between quotients with the same denominator, constant quotients hoisted per member; denominators that
+//     the reference masks afterwards (zeroref!: D == 0, h == 0, n + dn == 0, phi == 1) are replaced by 1 BEFORE
+//     the reciprocal so that open-water cells never enter the IEEE slow path (they did 13 times per cell-step in the
+//     literal flavour: 0/0 everywhere); unmasked special operands still take the literal x / y (rare branch);
+//   * the closure residual folded to (k/hp + B)*(Tm - T0) + (ai*S - A + f) + D nabla^2 Tbar, k/hp computed once
+//     per step, stencil coefficients pre-scaled by the member's D in per-warp shared memory;
+//   * FMA contraction.
+// Mapping (B200: 148 SMs x 4 sub-partitions x 16 FP64 lanes, 64K registers per SM):
+//   * one WARP integrates one member; lane l owns the K contiguous cells j = l*K .. l*K+K-1 (K = ceil(nx/32)); the
+//     six state vectors (Ei, Ew, h, D, phi, closure warm start T0) stay in registers for the whole launch;
+//   * no CTA barrier and no shared-memory exchange in the time loop: neighbour temperatures cross lanes with two
+//     shuffles per stencil evaluation, Newton convergence is a warp vote (every member iterates as often as it
+//     needs), the tridiagonal Jacobian system is solved partitioned -- K rows per lane with a left spike, parallel
+//     cyclic reduction over shuffles for the 32 interface unknowns, local back substitution;
+//   * geometry tables are per-CTA shared memory laid out [cell-in-lane][lane] (bank-conflict free);
+//   * cos(2*pi*t) comes from a per-step table built on the host (same libm as the oracle).
+// Results agree with the oracle to rounding over short horizons; the MIZ dynamics amplify rounding differences
+// (DESIGN.md "MIZ sensitivity"), so long runs are compared through the literal kernel instead.
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
 
-int ebm_launch_miz_fast(const MizKArgs& a, cudaStream_t stream) { return miz_launch_any(a, stream); }
+#include "ebm_internal.cuh"
+
+namespace {
+
+constexpr double kPi = 3.141592653589793;   // Float64(pi)
+constexpr unsigned kFull = 0xffffffffu;
+constexpr int kWarps = 4;                   // members per CTA
+
+__device__ __forceinline__ double shfl_up1(double v) { return __shfl_up_sync(kFull, v, 1); }
+__device__ __forceinline__ double shfl_dn1(double v) { return __shfl_down_sync(kFull, v, 1); }
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_min(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(kFull, v, o));
+  return v;
+}
+
+// reciprocal of an ordinary number (normal, 2^-1000 < |y| < 2^1000): ~1 ulp, no slow path
+__device__ __forceinline__ double rcp_nr(double y) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(y));
+  double e = fma(-y, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-y, r, 1.0);
+  r = fma(r, e, r);
+  return r;
+}
+__device__ __forceinline__ bool rcp_ok(double y) {
+  const unsigned e = ((unsigned)__double2hiint(y) >> 20) & 0x7ffu;
+  return (e - 24u) < 2000u;
+}
+__device__ __noinline__ double slow_div(double x, double y) { return x / y; }
+// x / y for any operands: the reciprocal path when y is an ordinary number (x = 0, Inf, NaN behave as in IEEE),
+// the literal division otherwise (y = 0, denormal, Inf, NaN, or extreme)
+__device__ __forceinline__ double fdiv(double x, double y) {
+  if (__builtin_expect(rcp_ok(y), 1)) return x * rcp_nr(y);
+  return slow_div(x, y);
+}
+
+template <int K>
+struct Tabs {   // per CTA, [i][lane] for cell j = lane*K + i
+  double x[K * 32], x2[K * 32], wts[K * 32];
+  double lo[kWarps][K * 32], up[kWarps][K * 32];   // member's D times the stencil coefficient towards j-1 / j+1
+  double cst[kWarps][48];                          // member constants (warp-uniform: broadcast loads, not registers)
+};
+
+// indices into Tabs::cst
+enum { cA, cB, ccw, cS0, cS1, cS2, ca0, ca2, cai, cFb, ck, cLf, cTm, cm1, calpha, cDmin, cDmax, chmin,
+       cTm_m2, cinv_alpha, cc_dn, cc_melt, cc_weld, cc_flat, cdt_Lf, ctwoLf, ctworl, cF0, cNCST = cF0 + EBM_NFORCING };
+
+// ---- D nabla^2 of a profile held K cells per lane:  up*(T[j+1]-T[j]) - lo*(T[j]-T[j-1])  (infrastructure.jl:495-527)
+template <int K>
+__device__ __forceinline__ void diffuse(const double* __restrict__ lo, const double* __restrict__ up, int lane,
+                                        const double (&tb)[K], double (&out)[K]) {
+  const double left = shfl_up1(tb[K - 1]);
+  const double right = shfl_dn1(tb[0]);
+#pragma unroll
+  for (int i = 0; i < K; ++i) {
+    const int s = i * 32 + lane;
+    const double tm = (i == 0) ? left : tb[i - 1];
+    const double tp = (i == K - 1) ? right : tb[i + 1];
+    out[i] = fma(up[s], tp - tb[i], -lo[s] * (tb[i] - tm));   // a zero coefficient silences the missing neighbour
+  }
+}
+
+// ---- tridiagonal solve across the warp, K rows per lane; rhs -> solution -----------------------------------------------
+template <int K>
+__device__ __forceinline__ void tridiag(int lane, const double (&jl)[K], const double (&jd)[K], const double (&ju)[K],
+                                        double (&rhs)[K]) {
+  // local forward elimination:  x_i + q_i x_{i+1} + s_i xL = y_i   (xL = last unknown of the previous lane)
+  double q[K], s[K];
+  {
+    double qp = 0.0, yp = 0.0, sp = 0.0;
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+      const double w = (i == 0) ? jd[i] : fma(-jl[i], qp, jd[i]);
+      const double iw = rcp_nr(w);
+      const double tq = jl[i] * iw;
+      q[i] = ju[i] * iw;
+      const double yi = (i == 0) ? rhs[i] * iw : fma(-tq, yp, rhs[i] * iw);
+      const double si = (i == 0) ? tq : -tq * sp;
+      s[i] = si; rhs[i] = yi;
+      qp = q[i]; yp = yi; sp = si;
+    }
+  }
+  // reduce row 0 to  x_0 = al - be*xL - ga*z   (z = my last unknown)
+  double al = rhs[K - 2], be = s[K - 2], ga = q[K - 2];
+#pragma unroll
+  for (int i = K - 3; i >= 0; --i) {
+    al = fma(-q[i], al, rhs[i]);
+    be = fma(-q[i], be, s[i]);
+    ga = -q[i] * ga;
+  }
+  // interface row of this lane:  A z_{l-1} + B z_l + C z_{l+1} = R, from the next lane's (al, be, ga)
+  const double nal = shfl_dn1(al), nbe = shfl_dn1(be), nga = shfl_dn1(ga);
+  const double ql = (lane == 31) ? 0.0 : q[K - 1];
+  double A = (lane == 0) ? 0.0 : s[K - 1];
+  double C = -ql * nga;
+  double R = fma(-ql, nal, rhs[K - 1]);
+  {
+    const double ib = rcp_nr(fma(-ql, nbe, 1.0));
+    A *= ib; C *= ib; R *= ib;
+  }
+  // parallel cyclic reduction, rows kept normalised (B = 1); out-of-range neighbours are identity rows
+#pragma unroll
+  for (int st = 1; st < 32; st <<= 1) {
+    const double Au = __shfl_up_sync(kFull, A, st), Cu = __shfl_up_sync(kFull, C, st), Ru = __shfl_up_sync(kFull, R, st);
+    const double Ad = __shfl_down_sync(kFull, A, st), Cd = __shfl_down_sync(kFull, C, st), Rd = __shfl_down_sync(kFull, R, st);
+    const double a_ = (lane >= st) ? A : 0.0, c_ = (lane + st < 32) ? C : 0.0;
+    const double ib = rcp_nr(fma(-a_, Cu, fma(-c_, Ad, 1.0)));
+    const double Rn = fma(-a_, Ru, fma(-c_, Rd, R));
+    A = -(a_ * Au) * ib;
+    C = -(c_ * Cd) * ib;
+    R = Rn * ib;
+  }
+  const double z = R;
+  const double zup = shfl_up1(z);              // every lane executes the shuffle (full mask)
+  const double xL = (lane == 0) ? 0.0 : zup;
+  double xn = z;
+  rhs[K - 1] = z;
+#pragma unroll
+  for (int i = K - 2; i >= 0; --i) {
+    xn = fma(-q[i], xn, fma(-s[i], xL, rhs[i]));
+    rhs[i] = xn;
+  }
+}
+
+// ---- field output of one cell for a member with L1/L2 output: savesol! (infrastructure.jl:549-591) --------------------
+// v = the ten stored variables of cell j (order of include/ebm_cuda.h EBM_MV_*)
+__device__ __forceinline__ void store_cell(const MizKArgs& a, int j, long long msel, int year, int ti, int season,
+                                           const double (&v)[EBM_MIZ_NVAR]) {
+  const int nx = a.nx, nt = a.nt;
+  if (a.raw != nullptr && (!a.lastonly || year == a.dur - 1)) {
+    const long long nraw = a.lastonly ? (long long)nt : (long long)nt * a.dur;
+    const long long rawidx = a.lastonly ? (ti - 1) : ((long long)year * nt + ti - 1);
+    double* o = a.raw + ((msel * nraw + rawidx) * EBM_MIZ_NVAR) * (long long)nx + j;
+#pragma unroll
+    for (int q = 0; q < EBM_MIZ_NVAR; ++q) o[(long long)q * nx] = v[q];
+  }
+  if (a.seasonal != nullptr) {
+    double* yr = a.seasonal + ((msel * a.dur + year) * 3) * (long long)EBM_MIZ_NVAR * nx + j;
+    // the annual-mean slot doubles as the running sum of the year (annusol.raw -> crossmean, :556-559, :583-588)
+    double* av = yr + 2LL * EBM_MIZ_NVAR * nx;
+#pragma unroll
+    for (int q = 0; q < EBM_MIZ_NVAR; ++q) {
+      double* c = av + (long long)q * nx;
+      const double sum = (ti == 1) ? v[q] : *c + v[q];
+      *c = (ti == nt) ? sum / (double)nt : sum;
+      if (season == 0 || season == 1) yr[((long long)season * EBM_MIZ_NVAR + q) * nx] = v[q];
+    }
+  }
+}
+
+template <int K, int MINB>
+__global__ void __launch_bounds__(kWarps * 32, MINB) miz_fast_kernel(const MizKArgs a) {
+  __shared__ Tabs<K> tabs;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nx = a.nx, nt = a.nt, kind = a.g.kind;
+  const long long nmem = a.nmem;
+  const long long m_raw = (long long)blockIdx.x * kWarps + warp;
+  const long long m = m_raw < nmem ? m_raw : nmem - 1;
+
+  for (int s = threadIdx.x; s < K * 32; s += blockDim.x) {
+    const int i = s >> 5, l = s & 31;
+    const int j = l * K + i;
+    const bool v = j < nx;
+    tabs.x[s] = v ? a.g.x[j] : 0.0;
+    tabs.x2[s] = v ? a.g.x2[j] : 0.0;
+    tabs.wts[s] = v ? a.g.wts[j] : 0.0;
+  }
+  {
+    const double Dm = a.par[0 * nmem + m];
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+      const int j = lane * K + i;
+      double cu = 0.0, cl = 0.0;
+      if (j < nx) {
+        if (kind == 1) {   // generic flux-form stencil, infrastructure.jl:510-524
+          cu = (j < nx - 1) ? a.g.mxxph[j] / a.g.diffx[j + 1] / a.g.phmmh[j] : 0.0;
+          cl = (j > 0) ? a.g.mxxmh[j] / a.g.diffx[j] / a.g.phmmh[j] : 0.0;
+        } else {           // get_diffop, infrastructure.jl:480-489
+          cu = a.g.lam_hi[j]; cl = a.g.lam_lo[j];
+        }
+      }
+      tabs.up[warp][i * 32 + lane] = Dm * cu;
+      tabs.lo[warp][i * 32 + lane] = Dm * cl;
+    }
+  }
+  __syncthreads();
+  if (m_raw >= nmem) return;   // whole warp; no CTA barrier follows
+  const double* __restrict__ lo = tabs.lo[warp];
+  const double* __restrict__ up = tabs.up[warp];
+
+  // ---- member constants (miz_paramset, infrastructure.jl:436-441) -> per-warp shared memory
+  const int nt_ = nt;
+  const double dt = 1.0 / nt_, ntd = (double)nt_;
+  if (lane == 0) {
+    const double* q = a.par + m;
+    double* c = tabs.cst[warp];
+    const double pLf = q[12 * nmem], pTm = q[13 * nmem], pm2 = q[15 * nmem], palpha = q[16 * nmem], prl = q[17 * nmem];
+    const double pDmin = q[18 * nmem], phmin = q[20 * nmem], pkappa = q[21 * nmem];
+    c[cA] = q[1 * nmem]; c[cB] = q[2 * nmem]; c[ccw] = q[3 * nmem]; c[cS0] = q[4 * nmem]; c[cS1] = q[5 * nmem];
+    c[cS2] = q[6 * nmem]; c[ca0] = q[7 * nmem]; c[ca2] = q[8 * nmem]; c[cai] = q[9 * nmem]; c[cFb] = q[10 * nmem];
+    c[ck] = q[11 * nmem]; c[cLf] = pLf; c[cTm] = pTm; c[cm1] = q[14 * nmem]; c[calpha] = palpha;
+    c[cDmin] = pDmin; c[cDmax] = q[19 * nmem]; c[chmin] = phmin;
+    c[cTm_m2] = pow(pTm, pm2);                                               // wlat :71 -- `Tm^m2` binds to Tm (sic)
+    c[cinv_alpha] = 1.0 / palpha;
+    c[cc_dn] = dt / (pLf * palpha * (pDmin * pDmin) * phmin);               // psinplus :127 times dt (:174)
+    c[cc_melt] = -kPi / 2.0 * palpha;                                        // :141 (sic)
+    c[cc_weld] = pkappa * palpha / 4;                                        // :143
+    c[cc_flat] = pLf * kPi * (1.0 / palpha);                                 // :104
+    c[cdt_Lf] = dt / pLf;                                                    // :139
+    c[ctwoLf] = 2 * pLf;
+    c[ctworl] = 2.0 * prl;
+    for (int r = 0; r < EBM_NFORCING; ++r) c[cF0 + r] = a.forc[(long long)r * nmem + m];
+  }
+  __syncwarp();
+  const volatile double* cst = tabs.cst[warp];
+#define CST(name) (cst[c##name])
+  const bool constf = cst[cF0 + 1] == cst[cF0] && cst[cF0 + 2] == cst[cF0] && cst[cF0 + 6] == 0.0 &&
+                      cst[cF0 + 7] == 0.0 && cst[cF0 + 8] == 0.0 && cst[cF0 + 9] == 0.0;
+
+  double Ei[K], Ew[K], h[K], D[K], phi[K], T0[K];
+#pragma unroll
+  for (int i = 0; i < K; ++i) {
+    const int j = lane * K + i;
+    const bool v = j < nx;
+    const long long o = (long long)j * nmem + m;
+    Ei[i] = v ? a.Ei[o] : 0.0; Ew[i] = v ? a.Ew[o] : 0.0; h[i] = v ? a.h[o] : 0.0;
+    D[i] = v ? a.D[o] : 0.0; phi[i] = v ? a.phi[o] : 0.0; T0[i] = v ? a.T0[o] : 0.0;
+  }
+  double accT = 0.0, accE = 0.0, accP = 0.0;   // running hemispheric sums of the year (annual means are linear)
+  unsigned icebits = 0u;
+
+  const bool sel = a.field_stride > 0 && (m % a.field_stride) == 0 && (a.seasonal != nullptr || a.raw != nullptr);
+  const long long msel = sel ? m / a.field_stride : 0;
+  long long iters_total = 0, fails_total = 0;
+  const long long step_stop = a.step_limit > 0 ? (long long)a.step_limit : 0x7fffffffffffffffLL;
+  const double tol = a.tol;
+  const int maxit = a.maxit;
+
+  for (int year = a.year0; year < a.year0 + a.nyears; ++year) {
+    for (int ti = 1; ti <= nt; ++ti) {
+      if ((long long)year * nt + ti > step_stop) break;   // ebm_options_t.step_limit (warp-uniform)
+      const double S1c = CST(S1) * __ldg(a.g.ctab + (ti - 1));                   // S1*cos(2*pi*t)
+      double f = cst[cF0];
+      if (!constf)
+        f = ebm_forcing_eval(cst[cF0], cst[cF0 + 1], cst[cF0 + 2], cst[cF0 + 3], cst[cF0 + 4], cst[cF0 + 6], cst[cF0 + 7],
+                             cst[cF0 + 8], cst[cF0 + 9],
+                             ebm_global_time((long long)year * nt + ti, nt));
+      const double fA = f - CST(A);
+      const int season = (ti == a.winter_inx) ? 0 : (ti == a.summer_inx) ? 1 : (ti == nt) ? 2 : -1;
+
+      // ---- temperatures and the closure's per-step constants (miz.jl:156-158, :33-60)
+      double Tw[K], omTw[K], kb[K], c0[K];
+#pragma unroll
+      for (int i = 0; i < K; ++i) {
+        const int s = i * 32 + lane;
+        const double om = 1 - phi[i];
+        const double v = CST(Tm) + fdiv(Ew[i], om * CST(cw));                        // water_temp :30
+        Tw[i] = (v != v) ? 0.0 : v;                                          // :157
+        omTw[i] = om * Tw[i];
+        const double hp = (h[i] == 0.0) ? CST(hmin) : h[i];                      // :51
+        kb[i] = fdiv(CST(k), hp) + CST(B);                                           // k/hp + B
+        const double S = fma(-CST(S2), tabs.x2[s], fma(-S1c, tabs.x[s], CST(S0)));   // :11
+        c0[i] = fma(CST(ai), S, fA);                                             // ai*S - A + f
+      }
+      // ---- solveTi: semi-smooth Newton on  (k/hp + B)(Tm - T0) + c0 + D nabla^2(phi*min(T0,Tm) + (1-phi)Tw) = 0
+      int it = 0, fail = 0;
+      for (;;) {
+        double tb[K], res[K];
+#pragma unroll
+        for (int i = 0; i < K; ++i) tb[i] = fma((T0[i] < CST(Tm)) ? T0[i] : CST(Tm), phi[i], omTw[i]);   // Tbar! :21-25
+        diffuse<K>(lo, up, lane, tb, res);
+        bool ok = true, nan = false;
+#pragma unroll
+        for (int i = 0; i < K; ++i) {
+          const double v = fma(kb[i], CST(Tm) - T0[i], c0[i] + res[i]);          // T0eq :39-43
+          res[i] = -v;
+          if (lane * K + i < nx) {
+            const double av = fabs(v);
+            nan = nan || (av != av);
+            ok = ok && (av <= tol);
+          }
+        }
+        if (__all_sync(kFull, ok)) break;
+        if (__any_sync(kFull, nan) || it >= maxit) { fail = 1; break; }
+        // generalised Jacobian  J = -diag(k/hp + B) + L*diag(phi*[T0 < Tm])
+        double g[K], jl[K], jd[K], ju[K];
+#pragma unroll
+        for (int i = 0; i < K; ++i) g[i] = (T0[i] < CST(Tm)) ? phi[i] : 0.0;
+        const double gleft = shfl_up1(g[K - 1]), gright = shfl_dn1(g[0]);
+#pragma unroll
+        for (int i = 0; i < K; ++i) {
+          const int s = i * 32 + lane;
+          const double l = lo[s], u = up[s];
+          jd[i] = fma(-(l + u), g[i], -kb[i]);
+          jl[i] = l * ((i == 0) ? gleft : g[i - 1]);
+          ju[i] = u * ((i == K - 1) ? gright : g[i + 1]);
+          if (lane * K + i >= nx) res[i] = 0.0;
+        }
+        tridiag<K>(lane, jl, jd, ju, res);
+#pragma unroll
+        for (int i = 0; i < K; ++i) T0[i] += res[i];
+        ++it;
+      }
+      iters_total += it;
+      fails_total += fail;
+
+      // ---- fluxes, enthalpy, floe size, thickness, concentration (:160-187)
+      double Ti[K], tb[K], dif[K];
+#pragma unroll
+      for (int i = 0; i < K; ++i) {
+        const double tmin = (T0[i] < CST(Tm)) ? T0[i] : ((T0[i] != T0[i]) ? T0[i] : CST(Tm));   // min(T0, Tm) :65
+        Ti[i] = (h[i] == 0.0) ? 0.0 : tmin;                                            // :66
+        tb[i] = fma(Ti[i], phi[i], omTw[i]);
+      }
+      diffuse<K>(lo, up, lane, tb, dif);
+
+      double dgT = 0.0, dgE = 0.0, dgP = 0.0, dgX = 2.0;
+#pragma unroll
+      for (int i = 0; i < K; ++i) {
+        const int sidx = i * 32 + lane;
+        const double xj = tabs.x[sidx], x2j = tabs.x2[sidx];
+        const double Eio = Ei[i], Ewo = Ew[i], ho = h[i], Do = D[i], pho = phi[i];
+        const double om = 1 - pho;
+        const bool noD = Do == 0.0, noh = ho == 0.0, one = pho == 1.0;
+        const double S = fma(-CST(S2), x2j, fma(-S1c, xj, CST(S0)));
+        const double common = (dif[i] - CST(B) * (tb[i] - CST(Tm))) + CST(Fb);                    // -(A + B(Tb-Tm)) + diffusion + Fb (+ fA below)
+        const double Fvi = c0[i] + common;                                            // :99-100 (ice)
+        const double Fvw = fma(fma(-CST(a2), x2j, CST(a0)), S, fA) + common;                  // (water)
+        const double wl = CST(m1) * (Tw[i] - CST(Tm_m2));                                      // :71
+        const double rD = rcp_nr(noD ? 1.0 : Do);
+        const double n = noD ? 0.0 : pho * (rD * rD) * CST(inv_alpha);                     // num :84-85
+        const double Flat = noD ? 0.0 : (pho * ho) * (wl * CST(c_flat)) * rD;              // :104-105
+        const double rEi = fma(fma(pho, Fvi, Flat), dt, Eio);                         // :137,148,166
+        const double rEw = fma(fma(om, Fvw, -Flat), dt, Ewo);                         // :138,148,167
+        const double cEi = rEi > 0.0 ? 0.0 : rEi, cEw = rEw < 0.0 ? 0.0 : rEw;        // redistributeE :110-111
+        const double psiEw_dt = rEw - cEw;
+        double Ei_n = cEi + psiEw_dt;
+        const double Ew_n = cEw + (rEi - cEi);
+        const double d2rl = Do + CST(tworl);
+        const double ring = CST(alpha) * n * fma(d2rl, d2rl, -Do * Do);                  // area_lead :91
+        const double Al = (ring < om) ? ring : om;                                    // :92
+        const double psiEw = psiEw_dt * ntd;                                          // psiEwdt / dt (:173)
+        const double Ql = one ? 0.0 : Al * rcp_nr(one ? 1.0 : om) * psiEw;            // split_psiEw :121-122
+        const double Qp = psiEw - Ql;
+        const double dn = -Qp * CST(c_dn);                                                 // :127,174
+        const double lat_grow = noh ? 0.0 : fdiv(-Do, noh ? 1.0 : CST(twoLf) * ho * pho) * Ql;   // :142,144
+        const double Dt = fma(CST(c_melt), wl, lat_grow) + CST(c_weld) * pho * (Do * Do * Do);  // :141-145
+        const double rDn = fma(Dt, dt, Do);                                           // :175
+        const double total = n + dn;
+        const bool tz = total == 0.0;
+        const double rt = fdiv(1.0, tz ? 1.0 : total);
+        double Dn = tz ? 0.0 : fma(n, rDn, dn * CST(Dmin)) * rt;                          // average :131-132
+        Dn = Dn > CST(Dmax) ? CST(Dmax) : (Dn < CST(Dmin) ? CST(Dmin) : Dn);                          // :177
+        if (Ei_n == 0.0) Dn = 0.0;                                                    // :178
+        double rh = fma(-Fvi, CST(dt_Lf), ho);                                             // :139,179
+        rh = rh < 0.0 ? 0.0 : rh;                                                     // :180
+        const double hn = tz ? 0.0 : fma(n, rh, dn * CST(hmin)) * rt;                     // :181
+        const bool hz = hn == 0.0;
+        double ph = hz ? 0.0 : fdiv(-Ei_n, hz ? 1.0 : CST(Lf) * hn);                      // concentration :75-76
+        if (ph > 1.0) ph = 1.0;                                                       // :77
+        if (hz) Ei_n = 0.0;                                                           // :185
+        const double omn = 1 - ph;
+        const double En = fma(ph, Ei_n, omn * Ew_n);                                  // :186
+        const double Tn = fma(Ti[i], ph, omn * Tw[i]);                                // :187
+        Ei[i] = Ei_n; Ew[i] = Ew_n; D[i] = Dn; h[i] = hn; phi[i] = ph;
+
+        // ---- sampling
+        const bool real = lane * K + i < nx;
+        const double wj = tabs.wts[sidx];
+        accT = fma(wj, Tn, accT); accE = fma(wj, En, accE); accP = fma(wj, ph, accP);
+        if (ph > 0.0 && real) icebits |= 1u << i;
+        if (season == 0 || season == 1) {
+          dgT = fma(wj, Tn, dgT); dgE = fma(wj, En, dgE); dgP = fma(wj, ph, dgP);
+          if (ph > 0.0 && real) dgX = fmin(dgX, xj);
+        } else if (season == 2) {
+          if (((icebits >> i) & 1u) != 0u) dgX = fmin(dgX, xj);
+        }
+        if (sel && real) {
+          double v[EBM_MIZ_NVAR];
+          v[EBM_MV_T] = Tn; v[EBM_MV_Ei] = Ei_n;
+          v[EBM_MV_Ti] = (Ei_n == 0.0) ? NAN : Ti[i];                                 // :193
+          v[EBM_MV_D] = Dn; v[EBM_MV_n] = n; v[EBM_MV_h] = hn; v[EBM_MV_phi] = ph;
+          v[EBM_MV_E] = En; v[EBM_MV_Ew] = Ew_n;
+          v[EBM_MV_Tw] = (ph > 0.99) ? NAN : Tw[i];                                   // :194
+          store_cell(a, lane * K + i, msel, year, ti, season, v);
+        }
+      }
+      if (season >= 0 && a.diag != nullptr) {
+        if (season == 2) {   // annual means: mean over the year of the hemispheric means (linear)
+          dgT = accT / ntd; dgE = accE / ntd; dgP = accP / ntd;
+        }
+        const double t0 = warp_sum(dgT), t1 = warp_sum(dgE), t2 = warp_sum(dgP), t3 = warp_min(dgX);
+        if (lane == 0) {
+          double* o = a.diag + ((m * a.dur + year) * 3 + season) * 4;
+          o[0] = t0; o[1] = t1; o[2] = 2.0 * kPi * t2; o[3] = (t3 > 1.5) ? 1.0 : t3;
+        }
+      }
+      if (ti == nt) { accT = accE = accP = 0.0; icebits = 0u; }
+    }
+  }
+
+  // ---- final state
+  bool bad = false;
+#pragma unroll
+  for (int i = 0; i < K; ++i) {
+    const int j = lane * K + i;
+    if (j < nx) {
+      const long long o = (long long)j * nmem + m;
+      a.Ei[o] = Ei[i]; a.Ew[o] = Ew[i]; a.h[o] = h[i]; a.D[o] = D[i]; a.phi[o] = phi[i]; a.T0[o] = T0[i];
+      bad = bad || !(fabs(Ei[i]) < 1e300) || !(fabs(Ew[i]) < 1e300) || !(fabs(h[i]) < 1e300) ||
+            !(fabs(D[i]) < 1e300) || !(fabs(phi[i]) < 1e300);
+    }
+  }
+  bad = __any_sync(kFull, bad);
+  if (lane == 0) {
+    if (a.newton_iters != nullptr) a.newton_iters[m] += iters_total;
+    if (a.nonconv != nullptr) a.nonconv[m] += fails_total;
+    if (bad && a.flags != nullptr) a.flags[m] |= 1;
+  }
+}
+
+template <int K, int MINB>
+int launch_k(const MizKArgs& a, cudaStream_t stream) {
+  const long long blocks = (a.nmem + kWarps - 1) / kWarps;
+  if (blocks > 0x7fffffffLL) { ebm_set_error("miz: too many members (%lld)", a.nmem); return EBM_ERR_INVALID; }
+  miz_fast_kernel<K, MINB><<<(unsigned)blocks, kWarps * 32, 0, stream>>>(a);
+  EBM_CUDA_TRY(cudaGetLastError());
+  ebm_count_launch();
+  return EBM_OK;
+}
+
+}  // namespace
+
+int ebm_launch_miz_fast(const MizKArgs& a, cudaStream_t stream) {
+  if (a.nx < 3) { ebm_set_error("miz: nx must be >= 3"); return EBM_ERR_INVALID; }
+  if (a.single_ti > 0) return ebm_launch_miz_strict(a, stream);
+  if (a.nx <= 64) return launch_k<2, 4>(a, stream);
+  if (a.nx <= 128) return launch_k<4, 4>(a, stream);
+  if (a.nx <= 192) {
+    // resident CTAs per SM (register cap 255 / 168 / 128): tuning knob, default = fastest measured
+    static const int minb = getenv("EBM_MIZ_MINB") ? atoi(getenv("EBM_MIZ_MINB")) : 3;
+    if (minb == 2) return launch_k<6, 2>(a, stream);
+    if (minb == 4) return launch_k<6, 4>(a, stream);
+    return launch_k<6, 3>(a, stream);
+  }
+  if (a.nx <= 256) return launch_k<8, 2>(a, stream);
+  ebm_set_error("miz: nx=%d > 256 not supported by the register-resident kernel", a.nx);
+  return EBM_ERR_UNSUPPORTED;
+}
 
 int ebm_launch_miz(const MizKArgs& a, int strict, cudaStream_t stream) {
   return strict ? ebm_launch_miz_strict(a, stream) : ebm_launch_miz_fast(a, stream);

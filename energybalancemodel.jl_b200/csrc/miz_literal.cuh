@@ -1,7 +1,9 @@
-// miz_kernel.cuh -- the marginal-ice-zone (MIZ) ensemble step kernel; included by miz_kernel.cu (fast flavour,
-// FMA contraction allowed, warp-parallel tridiagonal solve) and miz_strict.cu (EBM_MIZ_STRICT=1, compiled with
-// -fmad=false: literal operation order of the reference, serial Thomas solve -- for parity debugging and the
-// one-step entry point ebm_miz_step).
+// miz_literal.cuh -- the marginal-ice-zone (MIZ) ensemble step kernel written in the reference's operation order.
+// Included by miz_strict.cu with EBM_MIZ_STRICT=1 and compiled with -fmad=false: literal arithmetic, IEEE
+// division, serial Thomas solve in the oracle's order -- bit-identical to the oracle; used for parity debugging
+// (ebm_options_t.strict) and by the one-step entry point ebm_miz_step.  With EBM_MIZ_STRICT=0 the same source is
+// the first, unoptimised fast flavour (kept compilable as a reference point); the production fast kernel, same
+// mapping with the arithmetic restructured for the FP64 pipe, is miz_kernel.cu.
 //
 // Replaces, for a whole ensemble and many years per launch, the reference's
 //   integrate loop            src/infrastructure.jl:630-634
