@@ -21,6 +21,22 @@
 // Citations: src/classic.jl:43-65 (step), src/infrastructure.jl:549-591 (savesol!), SURVEY.md Appendix A.
 #include "ebm_internal.cuh"
 
+#ifdef EBM_PHASE_TIMING
+// dev instrumentation: cycles spent by each warp of CTA 0 between the marks of a step, summed over the launch
+__device__ unsigned long long g_phase_cycles[8][8];
+#define PHASE_MARK(k)                                                                         \
+  do {                                                                                        \
+    const long long _now = clock64();                                                         \
+    if (blockIdx.x == 0 && (threadIdx.x & 31) == 0)                                           \
+      atomicAdd(&g_phase_cycles[k][threadIdx.x >> 5], (unsigned long long)(_now - phase_t));  \
+    phase_t = _now;                                                                           \
+  } while (0)
+#define PHASE_BEGIN() long long phase_t = clock64()
+#else
+#define PHASE_MARK(k) do { } while (0)
+#define PHASE_BEGIN() do { } while (0)
+#endif
+
 namespace {
 
 constexpr double kTwoPi = 6.283185307179586;
@@ -42,7 +58,7 @@ __device__ __forceinline__ bool is_zero(double v) { return ((__double2hiint(v) <
 
 struct __align__(16) PhysTab { double S0x, S1x, aw, wts; };      // per cell
 struct __align__(16) ElimTab { double iw, tq, q, s; };           // per row: band-local no-mask elimination
-struct __align__(16) CoefTab { double kjj, aoff, coff, xedge; }; // per cell: masked path / sampling
+struct __align__(16) CoefTab { double kjj, aoff, coff, ac; };    // per cell, masked path: ac = aoff_j * coff_{j-1} (0 on a band's first row)
 
 template <int K, int WB, int MW>
 struct Ctx {
@@ -57,14 +73,17 @@ struct Ctx {
   bool active, sel, cta_fields;
   long long m, msel;
   // state
-  double E[K], Tg[K], sE[K], accT;
+  double E[K], Tg[K], accT;
+  double* sumE;   // [NXP][MW] running annual sum of E per cell (shared memory: keeps 2K registers free)
 
   // annual sums and (SLOW only) sampled output of cell i after its update: savesol! (infrastructure.jl:549-591)
   template <bool SLOW>
   __device__ __forceinline__ void sample(const ClassicKArgs& a, const int i, const double wj, const double En,
                                          const double T, const int season, const int ti, const int year,
                                          double& dgT, double& dgE, double& dgA, double& dgX) {
-    sE[i] += En;
+    const int eidx = (j0 + i) * MW + mi;
+    const double sEi = sumE[eidx] + En;
+    if (!SLOW) sumE[eidx] = sEi;
     accT = fma(wj, T, accT);
     if (SLOW) {
       const int nx = a.nx, nt = a.nt;
@@ -82,19 +101,19 @@ struct Ctx {
       if (season >= 0) {
         double vT = T, vE = En, vN = Eneg;
         if (season == 2) {                                          // annual mean (infrastructure.jl:583-588)
-          vE = sE[i] * inv_nt;
+          vE = sEi * inv_nt;
           if (cta_fields) { vT = sumT[sidx] * inv_nt; vN = sumH[sidx] * inv_nt; }
         }
         dgT = fma(wj, vT, dgT);
         dgE = fma(wj, vE, dgE);
-        if (vE < 0.0 && j < nx) { dgA += wj; dgX = fmin(dgX, coef[j].xedge); }
+        if (vE < 0.0 && j < nx) { dgA += wj; dgX = fmin(dgX, phys[j].S1x); }
         if (sel && a.seasonal != nullptr && j < nx) {
           double* o = a.seasonal + ((((msel * a.dur + year) * 3 + season) * 3) * (long long)nx) + j;
           o[0] = vE; o[nx] = vT; o[2 * nx] = -vN * inv_Lf;
         }
       }
+      sumE[eidx] = (ti == nt) ? 0.0 : sEi;
       if (ti == nt) {
-        sE[i] = 0.0;
         if (cta_fields) { sumT[sidx] = 0.0; sumH[sidx] = 0.0; }
       }
     }
@@ -110,6 +129,7 @@ struct Ctx {
     const int season = SLOW ? ((ti == a.winter_inx) ? 0 : (ti == a.summer_inx) ? 1 : (ti == nt) ? 2 : -1) : -1;
     double q[K], s[K];   // q[i]: diagonal decrement dc/(M - kLf/E) of a masked row (else 0); later pivots / spikes
     bool anymask = false;
+    PHASE_BEGIN();
     double dgT = 0.0, dgE = 0.0, dgA = 0.0, dgX = 2.0;
 
     // ---- physics (classic.jl:47-53) and the rows of the implicit system (:55-63)
@@ -186,6 +206,7 @@ struct Ctx {
     if (SLOW && season == 2) dgT = accT * inv_nt;   // mean over the year of the hemispheric mean (linear)
     if (SLOW && ti == nt) accT = 0.0;
 
+    PHASE_MARK(0);   // physics
     // ---- local elimination  x_i + q_i x_{i+1} + s_i xL = y_i  and reduction of row 0 to (al, be, ga)
     double* f6 = iface + (band * 6) * MW + mi;
     if (!anymask) {
@@ -204,19 +225,27 @@ struct Ctx {
       f6[0 * MW] = el.s; f6[1 * MW] = el.q; f6[2 * MW] = Tg[K - 1];
       f6[3 * MW] = al; f6[4 * MW] = bandc[2 * band]; f6[5 * MW] = bandc[2 * band + 1];
     } else {
-      double qprev = 0.0, yprev = 0.0, sprev = 0.0;
+      // pivots in determinant form: P_i = w_0 ... w_i obeys P_i = d_i P_{i-1} - (a_i c_{i-1}) P_{i-2}, one dependent FMA
+      // per row; the K reciprocals 1/w_i = P_{i-1}/P_i are then independent of each other (|w| ~ 50..250: no overflow)
+      double Pm2 = 1.0, Pm1 = 1.0;
 #pragma unroll
       for (int i = 0; i < K; ++i) {
         const CoefTab cf = coef[j0 + i];
         const double diag = cf.kjj - q[i];
-        const double w = (i == 0) ? diag : fma(-cf.aoff, qprev, diag);
-        const double iw = fast_rcp(w);
+        const double P = (i == 0) ? diag : fma(diag, Pm1, -(cf.ac * Pm2));
+        s[i] = Pm1 * fast_rcp(P);            // 1 / w_i
+        Pm2 = Pm1; Pm1 = P;
+      }
+      double yprev = 0.0, sprev = 0.0;
+#pragma unroll
+      for (int i = 0; i < K; ++i) {
+        const CoefTab cf = coef[j0 + i];
+        const double iw = s[i];
         const double tq = cf.aoff * iw;
-        const double qi = cf.coff * iw;
         const double yi = (i == 0) ? Tg[i] * iw : fma(-tq, yprev, Tg[i] * iw);
         const double si = (i == 0) ? tq : -tq * sprev;
-        q[i] = qi; s[i] = si; Tg[i] = yi;
-        qprev = qi; yprev = yi; sprev = si;
+        q[i] = cf.coff * iw; s[i] = si; Tg[i] = yi;
+        yprev = yi; sprev = si;
       }
       double al = Tg[K - 2], be = s[K - 2], ga = q[K - 2];
 #pragma unroll
@@ -232,7 +261,9 @@ struct Ctx {
       double* r4 = red + (band * 4) * MW + mi;
       r4[0 * MW] = dgT; r4[1 * MW] = dgE; r4[2 * MW] = dgA; r4[3 * MW] = dgX;
     }
+    PHASE_MARK(1);   // elimination + reduction
     __syncthreads();
+    PHASE_MARK(2);   // barrier 1 wait
     // ---- interface system: WB unknowns per member.  Warp 0 solves it with two lanes per member working from
     // both ends towards the middle ("burn at both ends"), pivots carried as determinants D_k so that the
     // only dependent chain is one DFMA per row; all reciprocals are independent of each other.
@@ -285,7 +316,9 @@ struct Ctx {
         o[0] = t0; o[1] = t1; o[2] = kTwoPi * t2; o[3] = (t3 > 1.5) ? 1.0 : t3;
       }
     }
+    PHASE_MARK(3);   // interface solve (warp 0) / nothing
     __syncthreads();
+    PHASE_MARK(4);   // barrier 2 wait
     // ---- back substitution with the true neighbours
     const double xL = (band > 0) ? zs[(band - 1) * MW + mi] : 0.0;
     double xn = zs[band * MW + mi];
@@ -304,6 +337,7 @@ struct Ctx {
         Tg[i] = xn;
       }
     }
+    PHASE_MARK(5);   // back substitution
   }
 };
 
@@ -311,7 +345,7 @@ template <int K, int WB, int MW>
 constexpr size_t uniform_smem_bytes(bool fields) {
   return (size_t)K * WB * (sizeof(PhysTab) + sizeof(ElimTab) + sizeof(CoefTab)) +
          sizeof(double) * ((size_t)2 * WB + (size_t)(WB + 1) * 6 * MW + (size_t)WB * MW * (1 + 4) + 10 * MW +
-                           (fields ? (size_t)2 * K * WB * MW : 0));
+                           (size_t)K * WB * MW + (fields ? (size_t)2 * K * WB * MW : 0));
 }
 
 template <int K, int WB, int MW, int MAXR>
@@ -346,7 +380,8 @@ __global__ void __maxnreg__(MAXR) classic_uniform_kernel(const ClassicKArgs a) {
   double* zs = iface + (WB + 1) * 6 * MW;                        // [WB][MW]
   double* red = zs + WB * MW;                                    // [WB][4][MW]
   double* fr = red + WB * 4 * MW;                                // [10][MW]
-  double* sumT = fr + 10 * MW;                                   // [NXP][MW], only if the CTA writes fields
+  double* sumE = fr + 10 * MW;                                   // [NXP][MW]
+  double* sumT = sumE + NXP * MW;                                // [NXP][MW], only if the CTA writes fields
   double* sumH = sumT + NXP * MW;
 
   const double pD = par[0], pA = par[1], pB = par[2], pcw = par[3], pS0 = par[4], pS1 = par[5], pS2 = par[6];
@@ -363,7 +398,8 @@ __global__ void __maxnreg__(MAXR) classic_uniform_kernel(const ClassicKArgs a) {
     const double ll = v ? a.g.lam_lo[j] : 0.0, lh = v ? a.g.lam_hi[j] : 0.0;
     PhysTab p; p.S0x = fma(-pS2, x2, pS0); p.S1x = xj; p.aw = fma(-pa2, x2, pa0); p.wts = v ? a.g.wts[j] : 0.0;
     phys[j] = p;
-    CoefTab c; c.kjj = fma(fac, ll + lh, one_dttau); c.aoff = -fac * ll; c.coff = -fac * lh; c.xedge = v ? xj : 2.0;
+    CoefTab c; c.kjj = fma(fac, ll + lh, one_dttau); c.aoff = -fac * ll; c.coff = -fac * lh;
+    c.ac = (j % K == 0) ? 0.0 : c.aoff * (-fac * (v ? a.g.lam_hi[j - 1] : 0.0));
     coef[j] = c;
   }
   for (int qd = tid; qd < 6 * MW; qd += blockDim.x) iface[WB * 6 * MW + qd] = 0.0;
@@ -396,7 +432,7 @@ __global__ void __maxnreg__(MAXR) classic_uniform_kernel(const ClassicKArgs a) {
 
   Ctx<K, WB, MW> cx;
   cx.phys = phys; cx.elim = elim; cx.coef = coef; cx.bandc = bandc;
-  cx.iface = iface; cx.zs = zs; cx.red = red; cx.sumT = sumT; cx.sumH = sumH;
+  cx.iface = iface; cx.zs = zs; cx.red = red; cx.sumE = sumE; cx.sumT = sumT; cx.sumH = sumH;
   cx.A = pA; cx.Fb = pFb; cx.ai = pai; cx.cg_tau = cg_tau; cx.M = pB + cg_tau; cx.kLf = pk * pLf;
   cx.inv_cw = 1.0 / pcw; cx.dt = dt; cx.dt_tau = dt_tau; cx.dttau_cw = dt_tau * cx.inv_cw; cx.dc = dt_tau * cg_tau;
   cx.inv_nt = 1.0 / nt; cx.inv_Lf = 1.0 / pLf;
@@ -413,7 +449,7 @@ __global__ void __maxnreg__(MAXR) classic_uniform_kernel(const ClassicKArgs a) {
     const bool v = j < nx;
     cx.E[i] = v ? a.E[(long long)j * nmem + m] : 1.0;     // pad cells: decoupled open-water rows
     cx.Tg[i] = v ? a.Tg[(long long)j * nmem + m] : 0.0;
-    cx.sE[i] = 0.0;
+    sumE[j * MW + mi] = 0.0;
     if (cx.cta_fields) { sumT[j * MW + mi] = 0.0; sumH[j * MW + mi] = 0.0; }
   }
   // Forcing{true}: base == peak == cool, all breakpoints 0 -> the call is the constant `base`
@@ -423,10 +459,13 @@ __global__ void __maxnreg__(MAXR) classic_uniform_kernel(const ClassicKArgs a) {
   const bool constf = __syncthreads_and(myconst) != 0;
   const bool has_raw = __syncthreads_or(cx.sel && (a.raw != nullptr)) != 0;
 
+  double S1c_next = pS1 * __ldg(a.g.ctab);   // S1*cos(2*pi*t_1); ctab[nt] == ctab[0] closes the year (classic.jl:25)
   for (int year = a.year0; year < a.year0 + a.nyears; ++year) {
     const bool raw_year = has_raw && (!a.lastonly || year == a.dur - 1);
     for (int ti = 1; ti <= nt; ++ti) {
-      const double S1c0 = pS1 * __ldg(a.g.ctab + (ti - 1)), S1c1 = pS1 * __ldg(a.g.ctab + ti);
+      // column i+1 of this step is column i of the next: one table load per step, consumed late in the step
+      const double S1c0 = S1c_next, S1c1 = pS1 * __ldg(a.g.ctab + ti);
+      S1c_next = S1c1;
       double f = fbase;
       if (!constf) {
         const long long tinx = (long long)year * nt + ti;
@@ -475,6 +514,19 @@ int launch_uniform(const ClassicKArgs& a, cudaStream_t stream) {
 }  // namespace
 
 int ebm_classic_uniform_max_nx() { return 104; }
+
+// dev: read and reset the phase counters (zeros unless built with -DEBM_PHASE_TIMING)
+extern "C" int ebm_debug_phase_cycles(unsigned long long* out64) {
+#ifdef EBM_PHASE_TIMING
+  if (cudaMemcpyFromSymbol(out64, g_phase_cycles, sizeof(unsigned long long) * 64) != cudaSuccess) return -2;
+  unsigned long long z[64] = {0};
+  cudaMemcpyToSymbol(g_phase_cycles, z, sizeof(z));
+  return 0;
+#else
+  for (int i = 0; i < 64; ++i) out64[i] = 0;
+  return 1;
+#endif
+}
 
 // variant: 0 = default.  Other values select alternative instantiations for tuning (env EBM_CLASSIC_VARIANT).
 int ebm_launch_classic_uniform(const ClassicKArgs& a, int variant, cudaStream_t stream) {
