@@ -127,6 +127,14 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- CPU arm
+def host_threads():
+    """All host cores this process may use (torchrun exports OMP_NUM_THREADS=1; the oracle sets its own count)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_run(workload, nmem_total, years, sample_members, threads):
     """Oracle (port of the reference algorithm) with OpenMP over members on a strided sample."""
     import ebm_b200 as ebm
@@ -152,7 +160,7 @@ def reference_arm(args, nmem, years):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads = oracle.max_threads()
+    threads = host_threads()
     sample = args.cpu_sample_members or (8 * threads if args.workload == "classic" else 2 * threads)
     yrs = years
     vals = []
@@ -316,7 +324,7 @@ def main():
     cpu = None
     if rank == 0 and not args.no_cpu:
         import oracle
-        thr = oracle.max_threads()
+        thr = host_threads()
         sample = args.cpu_sample_members or (8 * thr if args.workload == "classic" else 2 * thr)
         v, dt, desc = cpu_run(args.workload, total, years, sample, thr)
         cpu = {"value": v, "unit": "member-years/s", "cores": thr, "kind": "port", "sample": desc, "seconds": dt}

@@ -60,7 +60,22 @@ struct __align__(16) PhysTab { double S0x, S1x, aw, wts; };      // per cell
 struct __align__(16) ElimTab { double iw, tq, q, s; };           // per row: band-local no-mask elimination
 struct __align__(16) CoefTab { double kjj, aoff, coff, ac; };    // per cell, masked path: ac = aoff_j * coff_{j-1} (0 on a band's first row)
 
-template <int K, int WB, int MW>
+// rows of the band system that survive from the elimination to the back substitution: registers (QS_SMEM = false)
+// or thread-private shared memory [2K][threads] (conflict free), which frees 4K registers for more resident CTAs
+template <int K, bool QS_SMEM>
+struct RowStore {
+  double q_[QS_SMEM ? 1 : K], s_[QS_SMEM ? 1 : K];
+  double* base;
+  int stride;
+  __device__ __forceinline__ double& q(int i) {
+    if constexpr (QS_SMEM) return base[(2 * i) * stride]; else return q_[i];
+  }
+  __device__ __forceinline__ double& s(int i) {
+    if constexpr (QS_SMEM) return base[(2 * i + 1) * stride]; else return s_[i];
+  }
+};
+
+template <int K, int WB, int MW, bool QS_SMEM>
 struct Ctx {
   static constexpr int NXP = K * WB;
   // tables / scratch in shared memory
@@ -74,6 +89,7 @@ struct Ctx {
   long long m, msel;
   // state
   double E[K], Tg[K], accT;
+  RowStore<K, QS_SMEM> rs;
   double* sumE;   // [NXP][MW] running annual sum of E per cell (shared memory: keeps 2K registers free)
 
   // annual sums and (SLOW only) sampled output of cell i after its update: savesol! (infrastructure.jl:549-591)
@@ -127,7 +143,7 @@ struct Ctx {
     const double fmA = f - A;
     const double fmAFb = fmA + Fb;
     const int season = SLOW ? ((ti == a.winter_inx) ? 0 : (ti == a.summer_inx) ? 1 : (ti == nt) ? 2 : -1) : -1;
-    double q[K], s[K];   // q[i]: diagonal decrement dc/(M - kLf/E) of a masked row (else 0); later pivots / spikes
+    // rs.q(i): diagonal decrement dc/(M - kLf/E) of a masked row (else 0); later the pivots / spikes of the band
     bool anymask = false;
     PHASE_BEGIN();
     double dgT = 0.0, dgE = 0.0, dgA = 0.0, dgX = 2.0;
@@ -147,13 +163,14 @@ struct Ctx {
         const double Cb = fma(alpha, S, fma(cg_tau, Tgo, fmAFb));   // C + Fb                             :48
         const double T = Eo * inv_cw;                                                             //     :51
         const double En = fma(dt, fma(-M, T, Cb), Eo);                                            //     :53
-        q[i] = 0.0;
         E[i] = En;
         Tg[i] = fma(dttau_cw, En, Tgo);
         crossed = crossed || is_neg(En);
         sample<SLOW>(a, i, p.wts, En, T, season, ti, year, dgT, dgE, dgA, dgX);
       }
       if (crossed) {                                        // freeze-up inside this step (rare): literal mask
+#pragma unroll
+        for (int i = 0; i < K; ++i) rs.q(i) = 0.0;
 #pragma unroll
         for (int i = 0; i < K; ++i) {
           const double En = E[i];
@@ -167,7 +184,7 @@ struct Ctx {
             const double T0 = C / (M - kLf / Eo);                                                 //     :50
             if (T0 < 0.0) {
               const double r = En / fma(M, En, -kLf);
-              q[i] = dc * r; anymask = true;
+              rs.q(i) = dc * r; anymask = true;
               Tg[i] = fma(dt_tau * r, fma(ai, fma(-S1c1, p.S1x, p.S0x), fmA), Tgo);
             } else {
               Tg[i] = Tgo;
@@ -196,7 +213,7 @@ struct Ctx {
         const double r = En * fast_rcp(fma(M, En, -kLf));   // 1/(M - kLf/E)
         const double rhs_m = fma(dt_tau * r, fma(ai, fma(-S1c1, p.S1x, p.S0x), fmA), Tgo);        //     :58-62
         const double rhs_w = fma(dttau_cw, En, Tgo);
-        q[i] = masked ? dc * r : 0.0;                       // diag = kappa_jj - dc/(M - kLf/E)        :56
+        rs.q(i) = masked ? dc * r : 0.0;                       // diag = kappa_jj - dc/(M - kLf/E)        :56
         anymask = anymask || masked;
         E[i] = En;
         Tg[i] = masked ? rhs_m : (negn ? Tgo : rhs_w);
@@ -231,30 +248,30 @@ struct Ctx {
 #pragma unroll
       for (int i = 0; i < K; ++i) {
         const CoefTab cf = coef[j0 + i];
-        const double diag = cf.kjj - q[i];
+        const double diag = cf.kjj - rs.q(i);
         const double P = (i == 0) ? diag : fma(diag, Pm1, -(cf.ac * Pm2));
-        s[i] = Pm1 * fast_rcp(P);            // 1 / w_i
+        rs.s(i) = Pm1 * fast_rcp(P);            // 1 / w_i
         Pm2 = Pm1; Pm1 = P;
       }
       double yprev = 0.0, sprev = 0.0;
 #pragma unroll
       for (int i = 0; i < K; ++i) {
         const CoefTab cf = coef[j0 + i];
-        const double iw = s[i];
+        const double iw = rs.s(i);
         const double tq = cf.aoff * iw;
         const double yi = (i == 0) ? Tg[i] * iw : fma(-tq, yprev, Tg[i] * iw);
         const double si = (i == 0) ? tq : -tq * sprev;
-        q[i] = cf.coff * iw; s[i] = si; Tg[i] = yi;
+        rs.q(i) = cf.coff * iw; rs.s(i) = si; Tg[i] = yi;
         yprev = yi; sprev = si;
       }
-      double al = Tg[K - 2], be = s[K - 2], ga = q[K - 2];
+      double al = Tg[K - 2], be = rs.s(K - 2), ga = rs.q(K - 2);
 #pragma unroll
       for (int i = K - 3; i >= 0; --i) {
-        al = fma(-q[i], al, Tg[i]);
-        be = fma(-q[i], be, s[i]);
-        ga = -q[i] * ga;
+        al = fma(-rs.q(i), al, Tg[i]);
+        be = fma(-rs.q(i), be, rs.s(i));
+        ga = -rs.q(i) * ga;
       }
-      f6[0 * MW] = s[K - 1]; f6[1 * MW] = q[K - 1]; f6[2 * MW] = Tg[K - 1];
+      f6[0 * MW] = rs.s(K - 1); f6[1 * MW] = rs.q(K - 1); f6[2 * MW] = Tg[K - 1];
       f6[3 * MW] = al; f6[4 * MW] = be; f6[5 * MW] = ga;
     }
     if (SLOW && season >= 0) {
@@ -333,7 +350,7 @@ struct Ctx {
     } else {
 #pragma unroll
       for (int i = K - 2; i >= 0; --i) {
-        xn = fma(-q[i], xn, fma(-s[i], xL, Tg[i]));
+        xn = fma(-rs.q(i), xn, fma(-rs.s(i), xL, Tg[i]));
         Tg[i] = xn;
       }
     }
@@ -341,14 +358,15 @@ struct Ctx {
   }
 };
 
-template <int K, int WB, int MW>
+template <int K, int WB, int MW, bool QS_SMEM>
 constexpr size_t uniform_smem_bytes(bool fields) {
   return (size_t)K * WB * (sizeof(PhysTab) + sizeof(ElimTab) + sizeof(CoefTab)) +
          sizeof(double) * ((size_t)2 * WB + (size_t)(WB + 1) * 6 * MW + (size_t)WB * MW * (1 + 4) + 10 * MW +
-                           (size_t)K * WB * MW + (fields ? (size_t)2 * K * WB * MW : 0));
+                           (size_t)K * WB * MW + (fields ? (size_t)2 * K * WB * MW : 0) +
+                           (QS_SMEM ? (size_t)2 * K * WB * MW : 0));
 }
 
-template <int K, int WB, int MW, int MAXR>
+template <int K, int WB, int MW, int MAXR, bool QS_SMEM>
 __global__ void __maxnreg__(MAXR) classic_uniform_kernel(const ClassicKArgs a) {
   static_assert(MW == 16, "warp 0 = two lanes per member (full-warp shuffles)");
   static_assert(WB % 2 == 0 && (WB * MW) % 32 == 0, "whole warps, even band count");
@@ -381,7 +399,8 @@ __global__ void __maxnreg__(MAXR) classic_uniform_kernel(const ClassicKArgs a) {
   double* red = zs + WB * MW;                                    // [WB][4][MW]
   double* fr = red + WB * 4 * MW;                                // [10][MW]
   double* sumE = fr + 10 * MW;                                   // [NXP][MW]
-  double* sumT = sumE + NXP * MW;                                // [NXP][MW], only if the CTA writes fields
+  double* qsm = sumE + NXP * MW;                                 // [2K][threads] band rows (QS_SMEM only)
+  double* sumT = qsm + (QS_SMEM ? 2 * NXP * MW : 0);             // [NXP][MW], only if the launch writes fields
   double* sumH = sumT + NXP * MW;
 
   const double pD = par[0], pA = par[1], pB = par[2], pcw = par[3], pS0 = par[4], pS1 = par[5], pS2 = par[6];
@@ -430,7 +449,9 @@ __global__ void __maxnreg__(MAXR) classic_uniform_kernel(const ClassicKArgs a) {
     bandc[2 * b] = be; bandc[2 * b + 1] = ga;
   }
 
-  Ctx<K, WB, MW> cx;
+  Ctx<K, WB, MW, QS_SMEM> cx;
+  cx.rs.base = qsm + tid;
+  cx.rs.stride = WB * MW;
   cx.phys = phys; cx.elim = elim; cx.coef = coef; cx.bandc = bandc;
   cx.iface = iface; cx.zs = zs; cx.red = red; cx.sumE = sumE; cx.sumT = sumT; cx.sumH = sumH;
   cx.A = pA; cx.Fb = pFb; cx.ai = pai; cx.cg_tau = cg_tau; cx.M = pB + cg_tau; cx.kLf = pk * pLf;
@@ -492,15 +513,15 @@ __global__ void __maxnreg__(MAXR) classic_uniform_kernel(const ClassicKArgs a) {
   if (bad && a.flags != nullptr) atomicOr(a.flags + m, 1);
 }
 
-template <int K, int WB, int MW, int MAXR>
+template <int K, int WB, int MW, int MAXR, bool QS_SMEM = false>
 int launch_uniform(const ClassicKArgs& a, cudaStream_t stream) {
   if (a.nx > K * WB) {
     ebm_set_error("classic_uniform: nx=%d exceeds %d bands of %d cells", a.nx, WB, K);
     return EBM_ERR_UNSUPPORTED;
   }
   const bool fields = a.seasonal != nullptr && a.field_stride > 0;
-  const size_t smem = uniform_smem_bytes<K, WB, MW>(fields);
-  auto kern = classic_uniform_kernel<K, WB, MW, MAXR>;
+  const size_t smem = uniform_smem_bytes<K, WB, MW, QS_SMEM>(fields);
+  auto kern = classic_uniform_kernel<K, WB, MW, MAXR, QS_SMEM>;
   EBM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // leave room for several CTAs per SM: ask for the largest shared-memory carve-out (L1 is hardly used)
   EBM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -537,6 +558,11 @@ int ebm_launch_classic_uniform(const ClassicKArgs& a, int variant, cudaStream_t 
     case 2: return launch_uniform<13, 8, 16, 128>(a, stream);   // 4 warps / sub-partition: 4 CTAs per SM (spills)
     case 3: return launch_uniform<7, 16, 16, 128>(a, stream);   // 8 warps per CTA, 2 CTAs per SM
     case 4: return launch_uniform<7, 16, 16, 96>(a, stream);
-    default: return launch_uniform<13, 8, 16, 255>(a, stream);  // 2 warps / sub-partition: 2 CTAs per SM, no spills (fastest measured)
+    case 5: return launch_uniform<13, 8, 16, 255>(a, stream);         // band rows in registers: 2 CTAs per SM
+    case 6: return launch_uniform<13, 8, 16, 128, true>(a, stream);   // band rows in shared memory, 128 registers (spills)
+    case 7: return launch_uniform<13, 8, 16, 255, true>(a, stream);
+    // default: band rows (pivots / spikes) in thread-private shared memory, 168 registers -> 3 CTAs (12 warps) per SM:
+    // fastest measured at 65 536 members (826 k member-years/s vs 734 k with the rows in registers at 2 CTAs per SM)
+    default: return launch_uniform<13, 8, 16, 168, true>(a, stream);
   }
 }

@@ -252,8 +252,9 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) miz_fast_kernel(const MizKA
     for (int r = 0; r < EBM_NFORCING; ++r) c[cF0 + r] = a.forc[(long long)r * nmem + m];
   }
   __syncwarp();
-  const volatile double* cst = tabs.cst[warp];
+  const double* cst = tabs.cst[warp];   // re-read after every STEP_FENCE: constants are CSE'd within a phase only
 #define CST(name) (cst[c##name])
+#define STEP_FENCE() asm volatile("" ::: "memory")
   const bool constf = cst[cF0 + 1] == cst[cF0] && cst[cF0 + 2] == cst[cF0] && cst[cF0 + 6] == 0.0 &&
                       cst[cF0 + 7] == 0.0 && cst[cF0 + 8] == 0.0 && cst[cF0 + 9] == 0.0;
 
@@ -279,6 +280,7 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) miz_fast_kernel(const MizKA
   for (int year = a.year0; year < a.year0 + a.nyears; ++year) {
     for (int ti = 1; ti <= nt; ++ti) {
       if ((long long)year * nt + ti > step_stop) break;   // ebm_options_t.step_limit (warp-uniform)
+      STEP_FENCE();
       const double S1c = CST(S1) * __ldg(a.g.ctab + (ti - 1));                   // S1*cos(2*pi*t)
       double f = cst[cF0];
       if (!constf)
@@ -345,6 +347,7 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) miz_fast_kernel(const MizKA
       fails_total += fail;
 
       // ---- fluxes, enthalpy, floe size, thickness, concentration (:160-187)
+      STEP_FENCE();
       double Ti[K], tb[K], dif[K];
 #pragma unroll
       for (int i = 0; i < K; ++i) {

@@ -13,5 +13,5 @@ timeout 400 ncu --set full --clock-control none --import-source on -k regex:clas
 timeout 200 $MZ > $O/${tag}_miz_plain.log 2>&1 &&
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file $O/${tag}_miz_launches.csv $MZ > $O/${tag}_miz_ncu1.log 2>&1
 timeout 200 $MZ > /dev/null 2>&1 &&
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:miz_warp -s 1 -c 1 -f -o $O/${tag}_miz_full $MZ > $O/${tag}_miz_ncu2.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:miz_ -s 1 -c 1 -f -o $O/${tag}_miz_full $MZ > $O/${tag}_miz_ncu2.log 2>&1
 tail -2 $O/${tag}_classic_plain.log $O/${tag}_miz_plain.log
