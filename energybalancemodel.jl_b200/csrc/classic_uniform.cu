@@ -64,9 +64,14 @@ struct __align__(16) CoefTab { double kjj, aoff, coff, ac; };    // per cell, ma
 // or thread-private shared memory [2K][threads] (conflict free), which frees 4K registers for more resident CTAs
 template <int K, bool QS_SMEM>
 struct RowStore {
-  double q_[QS_SMEM ? 1 : K], s_[QS_SMEM ? 1 : K];
+  double q_[QS_SMEM ? 1 : K], s_[QS_SMEM ? 1 : K], r_[QS_SMEM ? 1 : K];
   double* base;
   int stride;
+  // r(i) = E_i / (M E_i - kLf) = 1/(M - kLf/E_i) of the cell's CURRENT enthalpy, carried from step to step: this
+  // step's T0 = C/(M - kLf/E) (classic.jl:50) is C*r of the previous step's update (:56-62 computes it anyway)
+  __device__ __forceinline__ double& r(int i) {
+    if constexpr (QS_SMEM) return base[(2 * K + i) * stride]; else return r_[i];
+  }
   __device__ __forceinline__ double& q(int i) {
     if constexpr (QS_SMEM) return base[(2 * i) * stride]; else return q_[i];
   }
@@ -182,8 +187,9 @@ struct Ctx {
             const double Eo = fma(-dt, Cb, En) / fma(-dt * M, inv_cw, 1.0);
             const double C = Cb - Fb;
             const double T0 = C / (M - kLf / Eo);                                                 //     :50
+            const double r = En * fast_rcp(fma(M, En, -kLf));
+            rs.r(i) = r;
             if (T0 < 0.0) {
-              const double r = En / fma(M, En, -kLf);
               rs.q(i) = dc * r; anymask = true;
               Tg[i] = fma(dt_tau * r, fma(ai, fma(-S1c1, p.S1x, p.S0x), fmA), Tgo);
             } else {
@@ -201,19 +207,19 @@ struct Ctx {
         const bool ice = is_neg(Eo);
         const double alpha = ice ? ai : (is_zero(Eo) ? 0.0 : p.aw);                               //     :47
         const double C = fma(alpha, S, fma(cg_tau, Tgo, fmA));                                    //     :48
-        const double den = fma(M, Eo, -kLf);                // T0 = C/(M - kLf/E) = C*E/(M*E - kLf)    :50
-        const double T0 = (C * Eo) * fast_rcp(den);
-        const bool Cneg = C < 0.0;                          // for E < 0: den < 0, so T0 < 0 <=> C < 0
+        const double T0 = C * rs.r(i);                      // T0 = C/(M - kLf/E), 1/(M - kLf/E) carried     :50
+        const bool Cneg = C < 0.0;                          // for E < 0: M - kLf/E > 0, so T0 < 0 <=> C < 0
         const double T = ice ? (Cneg ? T0 : 0.0) : Eo * inv_cw;                                   //     :51
         const double En = fma(dt, fma(-M, T, C) + Fb, Eo);                                        //     :53
         const bool negn = is_neg(En);
         // sign of T0 for a water cell that freezes in this step: sign(C) * sign(M - kLf/E), E > 0
-        const bool T0neg = ice ? Cneg : (!is_zero(Eo) && (Cneg != is_neg(den)) && C != 0.0);
+        const bool T0neg = ice ? Cneg : (!is_zero(Eo) && (Cneg != is_neg(fma(M, Eo, -kLf))) && C != 0.0);
         const bool masked = T0neg && negn;                  // (T0<0) & (E<0), E updated               :56,61
         const double r = En * fast_rcp(fma(M, En, -kLf));   // 1/(M - kLf/E)
         const double rhs_m = fma(dt_tau * r, fma(ai, fma(-S1c1, p.S1x, p.S0x), fmA), Tgo);        //     :58-62
         const double rhs_w = fma(dttau_cw, En, Tgo);
         rs.q(i) = masked ? dc * r : 0.0;                       // diag = kappa_jj - dc/(M - kLf/E)        :56
+        rs.r(i) = r;
         anymask = anymask || masked;
         E[i] = En;
         Tg[i] = masked ? rhs_m : (negn ? Tgo : rhs_w);
@@ -363,7 +369,7 @@ constexpr size_t uniform_smem_bytes(bool fields) {
   return (size_t)K * WB * (sizeof(PhysTab) + sizeof(ElimTab) + sizeof(CoefTab)) +
          sizeof(double) * ((size_t)2 * WB + (size_t)(WB + 1) * 6 * MW + (size_t)WB * MW * (1 + 4) + 10 * MW +
                            (size_t)K * WB * MW + (fields ? (size_t)2 * K * WB * MW : 0) +
-                           (QS_SMEM ? (size_t)2 * K * WB * MW : 0));
+                           (QS_SMEM ? (size_t)3 * K * WB * MW : 0));
 }
 
 template <int K, int WB, int MW, int MAXR, bool QS_SMEM>
@@ -399,8 +405,8 @@ __global__ void __maxnreg__(MAXR) classic_uniform_kernel(const ClassicKArgs a) {
   double* red = zs + WB * MW;                                    // [WB][4][MW]
   double* fr = red + WB * 4 * MW;                                // [10][MW]
   double* sumE = fr + 10 * MW;                                   // [NXP][MW]
-  double* qsm = sumE + NXP * MW;                                 // [2K][threads] band rows (QS_SMEM only)
-  double* sumT = qsm + (QS_SMEM ? 2 * NXP * MW : 0);             // [NXP][MW], only if the launch writes fields
+  double* qsm = sumE + NXP * MW;                                 // [3K][threads] band rows q, s, r (QS_SMEM only)
+  double* sumT = qsm + (QS_SMEM ? 3 * NXP * MW : 0);             // [NXP][MW], only if the launch writes fields
   double* sumH = sumT + NXP * MW;
 
   const double pD = par[0], pA = par[1], pB = par[2], pcw = par[3], pS0 = par[4], pS1 = par[5], pS2 = par[6];
@@ -471,6 +477,7 @@ __global__ void __maxnreg__(MAXR) classic_uniform_kernel(const ClassicKArgs a) {
     cx.E[i] = v ? a.E[(long long)j * nmem + m] : 1.0;     // pad cells: decoupled open-water rows
     cx.Tg[i] = v ? a.Tg[(long long)j * nmem + m] : 0.0;
     sumE[j * MW + mi] = 0.0;
+    cx.rs.r(i) = cx.E[i] * fast_rcp(fma(cx.M, cx.E[i], -cx.kLf));   // same expression as in the step: r is a pure function of E
     if (cx.cta_fields) { sumT[j * MW + mi] = 0.0; sumH[j * MW + mi] = 0.0; }
   }
   // Forcing{true}: base == peak == cool, all breakpoints 0 -> the call is the constant `base`
