@@ -62,16 +62,17 @@ __device__ __forceinline__ double rcp_nr(double y) {
   r = fma(r, e, r);
   return r;
 }
-__device__ __forceinline__ bool rcp_ok(double y) {
-  const unsigned e = ((unsigned)__double2hiint(y) >> 20) & 0x7ffu;
-  return (e - 24u) < 2000u;
-}
-__device__ __noinline__ double slow_div(double x, double y) { return x / y; }
-// x / y for any operands: the reciprocal path when y is an ordinary number (x = 0, Inf, NaN behave as in IEEE),
-// the literal division otherwise (y = 0, denormal, Inf, NaN, or extreme)
-__device__ __forceinline__ double fdiv(double x, double y) {
-  if (__builtin_expect(rcp_ok(y), 1)) return x * rcp_nr(y);
-  return slow_div(x, y);
+// zero / sign tests on the integer pipe (the FP64 pipe is the bottleneck); +0 and -0 are both zero
+__device__ __forceinline__ bool is_zero(double v) { return ((__double2hiint(v) << 1) | __double2loint(v)) == 0; }
+// x / y with y an ordinary non-zero number (no denormal / huge denominators: DESIGN.md 4.3)
+__device__ __forceinline__ double div_n(double x, double y) { return x * rcp_nr(y); }
+// x / y with y zero or ordinary: IEEE results for y == +-0 (x/0 = +-Inf, 0/0 = NaN/0 = NaN), branch free
+__device__ __forceinline__ double div_z(double x, double y) {
+  const bool z = is_zero(y);
+  const double q = x * rcp_nr(z ? 1.0 : y);
+  const double inf = __hiloint2double(0x7ff00000 | ((__double2hiint(x) ^ __double2hiint(y)) & 0x80000000), 0);
+  const double zq = (is_zero(x) || x != x) ? __longlong_as_double(0x7ff8000000000000LL) : inf;
+  return z ? zq : q;
 }
 
 template <int K>
@@ -296,11 +297,11 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) miz_fast_kernel(const MizKA
       for (int i = 0; i < K; ++i) {
         const int s = i * 32 + lane;
         const double om = 1 - phi[i];
-        const double v = CST(Tm) + fdiv(Ew[i], om * CST(cw));                        // water_temp :30
+        const double v = CST(Tm) + div_z(Ew[i], om * CST(cw));                        // water_temp :30
         Tw[i] = (v != v) ? 0.0 : v;                                          // :157
         omTw[i] = om * Tw[i];
-        const double hp = (h[i] == 0.0) ? CST(hmin) : h[i];                      // :51
-        kb[i] = fdiv(CST(k), hp) + CST(B);                                           // k/hp + B
+        const double hp = is_zero(h[i]) ? CST(hmin) : h[i];                      // :51
+        kb[i] = div_n(CST(k), hp) + CST(B);                                           // k/hp + B
         const double S = fma(-CST(S2), tabs.x2[s], fma(-S1c, tabs.x[s], CST(S0)));   // :11
         c0[i] = fma(CST(ai), S, fA);                                             // ai*S - A + f
       }
@@ -339,9 +340,20 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) miz_fast_kernel(const MizKA
           if (lane * K + i >= nx) res[i] = 0.0;
         }
         tridiag<K>(lane, jl, jd, ju, res);
+        // The residual is piecewise linear: if the step leaves the active set [T0 < Tm] (where phi != 0) unchanged,
+        // the new T0 is the root to rounding (|res| ~ 1e-12 << tol) and the confirming residual evaluation the
+        // reference performs is skipped; the iteration count is the same either way.
+        bool changed = false, bad = false;
 #pragma unroll
-        for (int i = 0; i < K; ++i) T0[i] += res[i];
+        for (int i = 0; i < K; ++i) {
+          const double tn = T0[i] + res[i];
+          changed = changed || (!is_zero(phi[i]) && ((T0[i] < CST(Tm)) != (tn < CST(Tm))));
+          bad = bad || (tn != tn);
+          T0[i] = tn;
+        }
         ++it;
+        if (__any_sync(kFull, bad)) { fail = 1; break; }
+        if (!__any_sync(kFull, changed)) break;
       }
       iters_total += it;
       fails_total += fail;
@@ -352,7 +364,7 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) miz_fast_kernel(const MizKA
 #pragma unroll
       for (int i = 0; i < K; ++i) {
         const double tmin = (T0[i] < CST(Tm)) ? T0[i] : ((T0[i] != T0[i]) ? T0[i] : CST(Tm));   // min(T0, Tm) :65
-        Ti[i] = (h[i] == 0.0) ? 0.0 : tmin;                                            // :66
+        Ti[i] = is_zero(h[i]) ? 0.0 : tmin;                                            // :66
         tb[i] = fma(Ti[i], phi[i], omTw[i]);
       }
       diffuse<K>(lo, up, lane, tb, dif);
@@ -364,7 +376,7 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) miz_fast_kernel(const MizKA
         const double xj = tabs.x[sidx], x2j = tabs.x2[sidx];
         const double Eio = Ei[i], Ewo = Ew[i], ho = h[i], Do = D[i], pho = phi[i];
         const double om = 1 - pho;
-        const bool noD = Do == 0.0, noh = ho == 0.0, one = pho == 1.0;
+        const bool noD = is_zero(Do), noh = is_zero(ho), one = pho == 1.0;
         const double S = fma(-CST(S2), x2j, fma(-S1c, xj, CST(S0)));
         const double common = (dif[i] - CST(B) * (tb[i] - CST(Tm))) + CST(Fb);                    // -(A + B(Tb-Tm)) + diffusion + Fb (+ fA below)
         const double Fvi = c0[i] + common;                                            // :99-100 (ice)
@@ -386,20 +398,20 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) miz_fast_kernel(const MizKA
         const double Ql = one ? 0.0 : Al * rcp_nr(one ? 1.0 : om) * psiEw;            // split_psiEw :121-122
         const double Qp = psiEw - Ql;
         const double dn = -Qp * CST(c_dn);                                                 // :127,174
-        const double lat_grow = noh ? 0.0 : fdiv(-Do, noh ? 1.0 : CST(twoLf) * ho * pho) * Ql;   // :142,144
+        const double lat_grow = noh ? 0.0 : div_z(-Do, noh ? 1.0 : CST(twoLf) * ho * pho) * Ql;   // :142,144
         const double Dt = fma(CST(c_melt), wl, lat_grow) + CST(c_weld) * pho * (Do * Do * Do);  // :141-145
         const double rDn = fma(Dt, dt, Do);                                           // :175
         const double total = n + dn;
-        const bool tz = total == 0.0;
-        const double rt = fdiv(1.0, tz ? 1.0 : total);
+        const bool tz = is_zero(total);
+        const double rt = rcp_nr(tz ? 1.0 : total);
         double Dn = tz ? 0.0 : fma(n, rDn, dn * CST(Dmin)) * rt;                          // average :131-132
         Dn = Dn > CST(Dmax) ? CST(Dmax) : (Dn < CST(Dmin) ? CST(Dmin) : Dn);                          // :177
-        if (Ei_n == 0.0) Dn = 0.0;                                                    // :178
+        if (is_zero(Ei_n)) Dn = 0.0;                                                   // :178
         double rh = fma(-Fvi, CST(dt_Lf), ho);                                             // :139,179
         rh = rh < 0.0 ? 0.0 : rh;                                                     // :180
         const double hn = tz ? 0.0 : fma(n, rh, dn * CST(hmin)) * rt;                     // :181
-        const bool hz = hn == 0.0;
-        double ph = hz ? 0.0 : fdiv(-Ei_n, hz ? 1.0 : CST(Lf) * hn);                      // concentration :75-76
+        const bool hz = is_zero(hn);
+        double ph = hz ? 0.0 : div_n(-Ei_n, hz ? 1.0 : CST(Lf) * hn);                      // concentration :75-76
         if (ph > 1.0) ph = 1.0;                                                       // :77
         if (hz) Ei_n = 0.0;                                                           // :185
         const double omn = 1 - ph;
@@ -421,7 +433,7 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) miz_fast_kernel(const MizKA
         if (sel && real) {
           double v[EBM_MIZ_NVAR];
           v[EBM_MV_T] = Tn; v[EBM_MV_Ei] = Ei_n;
-          v[EBM_MV_Ti] = (Ei_n == 0.0) ? NAN : Ti[i];                                 // :193
+          v[EBM_MV_Ti] = is_zero(Ei_n) ? NAN : Ti[i];                                 // :193
           v[EBM_MV_D] = Dn; v[EBM_MV_n] = n; v[EBM_MV_h] = hn; v[EBM_MV_phi] = ph;
           v[EBM_MV_E] = En; v[EBM_MV_Ew] = Ew_n;
           v[EBM_MV_Tw] = (ph > 0.99) ? NAN : Tw[i];                                   // :194
