@@ -80,6 +80,7 @@ struct Tabs {   // per CTA, [i][lane] for cell j = lane*K + i
   double x[K * 32], x2[K * 32], wts[K * 32];
   double lo[kWarps][K * 32], up[kWarps][K * 32];   // member's D times the stencil coefficient towards j-1 / j+1
   double cst[kWarps][48];                          // member constants (warp-uniform: broadcast loads, not registers)
+  double cold[kWarps][5 * K * 32];                 // Ei, Ew, D, h, Tw: touched once or twice per step -> thread-private smem
 };
 
 // indices into Tabs::cst
@@ -191,7 +192,8 @@ __device__ __forceinline__ void store_cell(const MizKArgs& a, int j, long long m
 
 template <int K, int MINB>
 __global__ void __launch_bounds__(kWarps * 32, MINB) miz_fast_kernel(const MizKArgs a) {
-  __shared__ Tabs<K> tabs;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Tabs<K>& tabs = *reinterpret_cast<Tabs<K>*>(smem_raw);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nx = a.nx, nt = a.nt, kind = a.g.kind;
   const long long nmem = a.nmem;
@@ -259,14 +261,22 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) miz_fast_kernel(const MizKA
   const bool constf = cst[cF0 + 1] == cst[cF0] && cst[cF0 + 2] == cst[cF0] && cst[cF0 + 6] == 0.0 &&
                       cst[cF0 + 7] == 0.0 && cst[cF0 + 8] == 0.0 && cst[cF0 + 9] == 0.0;
 
-  double Ei[K], Ew[K], h[K], D[K], phi[K], T0[K];
+  // Ei, Ew and D are read and written once per step (outside the closure): they live in thread-private shared
+  // memory [array][i][lane]; h, phi and the warm start T0 stay in registers
+  double* const cold = tabs.cold[warp] + lane;
+#define EI(i) cold[(0 * K + (i)) * 32]
+#define EW(i) cold[(1 * K + (i)) * 32]
+#define DD(i) cold[(2 * K + (i)) * 32]
+#define HH(i) cold[(3 * K + (i)) * 32]
+#define TW(i) cold[(4 * K + (i)) * 32]
+  double phi[K], T0[K];
 #pragma unroll
   for (int i = 0; i < K; ++i) {
     const int j = lane * K + i;
     const bool v = j < nx;
     const long long o = (long long)j * nmem + m;
-    Ei[i] = v ? a.Ei[o] : 0.0; Ew[i] = v ? a.Ew[o] : 0.0; h[i] = v ? a.h[o] : 0.0;
-    D[i] = v ? a.D[o] : 0.0; phi[i] = v ? a.phi[o] : 0.0; T0[i] = v ? a.T0[o] : 0.0;
+    EI(i) = v ? a.Ei[o] : 0.0; EW(i) = v ? a.Ew[o] : 0.0; HH(i) = v ? a.h[o] : 0.0;
+    DD(i) = v ? a.D[o] : 0.0; phi[i] = v ? a.phi[o] : 0.0; T0[i] = v ? a.T0[o] : 0.0;
   }
   double accT = 0.0, accE = 0.0, accP = 0.0;   // running hemispheric sums of the year (annual means are linear)
   unsigned icebits = 0u;
@@ -292,15 +302,16 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) miz_fast_kernel(const MizKA
       const int season = (ti == a.winter_inx) ? 0 : (ti == a.summer_inx) ? 1 : (ti == nt) ? 2 : -1;
 
       // ---- temperatures and the closure's per-step constants (miz.jl:156-158, :33-60)
-      double Tw[K], omTw[K], kb[K], c0[K];
+      double omTw[K], kb[K], c0[K];
 #pragma unroll
       for (int i = 0; i < K; ++i) {
         const int s = i * 32 + lane;
         const double om = 1 - phi[i];
-        const double v = CST(Tm) + div_z(Ew[i], om * CST(cw));                        // water_temp :30
-        Tw[i] = (v != v) ? 0.0 : v;                                          // :157
-        omTw[i] = om * Tw[i];
-        const double hp = is_zero(h[i]) ? CST(hmin) : h[i];                      // :51
+        const double v = CST(Tm) + div_z(EW(i), om * CST(cw));                        // water_temp :30
+        const double tw = (v != v) ? 0.0 : v;                                  // :157
+        TW(i) = tw;
+        omTw[i] = om * tw;
+        const double hp = is_zero(HH(i)) ? CST(hmin) : HH(i);                      // :51
         kb[i] = div_n(CST(k), hp) + CST(B);                                           // k/hp + B
         const double S = fma(-CST(S2), tabs.x2[s], fma(-S1c, tabs.x[s], CST(S0)));   // :11
         c0[i] = fma(CST(ai), S, fA);                                             // ai*S - A + f
@@ -364,7 +375,7 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) miz_fast_kernel(const MizKA
 #pragma unroll
       for (int i = 0; i < K; ++i) {
         const double tmin = (T0[i] < CST(Tm)) ? T0[i] : ((T0[i] != T0[i]) ? T0[i] : CST(Tm));   // min(T0, Tm) :65
-        Ti[i] = is_zero(h[i]) ? 0.0 : tmin;                                            // :66
+        Ti[i] = is_zero(HH(i)) ? 0.0 : tmin;                                            // :66
         tb[i] = fma(Ti[i], phi[i], omTw[i]);
       }
       diffuse<K>(lo, up, lane, tb, dif);
@@ -374,14 +385,14 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) miz_fast_kernel(const MizKA
       for (int i = 0; i < K; ++i) {
         const int sidx = i * 32 + lane;
         const double xj = tabs.x[sidx], x2j = tabs.x2[sidx];
-        const double Eio = Ei[i], Ewo = Ew[i], ho = h[i], Do = D[i], pho = phi[i];
+        const double Eio = EI(i), Ewo = EW(i), ho = HH(i), Do = DD(i), pho = phi[i];
         const double om = 1 - pho;
         const bool noD = is_zero(Do), noh = is_zero(ho), one = pho == 1.0;
         const double S = fma(-CST(S2), x2j, fma(-S1c, xj, CST(S0)));
         const double common = (dif[i] - CST(B) * (tb[i] - CST(Tm))) + CST(Fb);                    // -(A + B(Tb-Tm)) + diffusion + Fb (+ fA below)
         const double Fvi = c0[i] + common;                                            // :99-100 (ice)
         const double Fvw = fma(fma(-CST(a2), x2j, CST(a0)), S, fA) + common;                  // (water)
-        const double wl = CST(m1) * (Tw[i] - CST(Tm_m2));                                      // :71
+        const double wl = CST(m1) * (TW(i) - CST(Tm_m2));                                      // :71
         const double rD = rcp_nr(noD ? 1.0 : Do);
         const double n = noD ? 0.0 : pho * (rD * rD) * CST(inv_alpha);                     // num :84-85
         const double Flat = noD ? 0.0 : (pho * ho) * (wl * CST(c_flat)) * rD;              // :104-105
@@ -416,8 +427,8 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) miz_fast_kernel(const MizKA
         if (hz) Ei_n = 0.0;                                                           // :185
         const double omn = 1 - ph;
         const double En = fma(ph, Ei_n, omn * Ew_n);                                  // :186
-        const double Tn = fma(Ti[i], ph, omn * Tw[i]);                                // :187
-        Ei[i] = Ei_n; Ew[i] = Ew_n; D[i] = Dn; h[i] = hn; phi[i] = ph;
+        const double Tn = fma(Ti[i], ph, omn * TW(i));                                // :187
+        EI(i) = Ei_n; EW(i) = Ew_n; DD(i) = Dn; HH(i) = hn; phi[i] = ph;
 
         // ---- sampling
         const bool real = lane * K + i < nx;
@@ -436,7 +447,7 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) miz_fast_kernel(const MizKA
           v[EBM_MV_Ti] = is_zero(Ei_n) ? NAN : Ti[i];                                 // :193
           v[EBM_MV_D] = Dn; v[EBM_MV_n] = n; v[EBM_MV_h] = hn; v[EBM_MV_phi] = ph;
           v[EBM_MV_E] = En; v[EBM_MV_Ew] = Ew_n;
-          v[EBM_MV_Tw] = (ph > 0.99) ? NAN : Tw[i];                                   // :194
+          v[EBM_MV_Tw] = (ph > 0.99) ? NAN : TW(i);                                   // :194
           store_cell(a, lane * K + i, msel, year, ti, season, v);
         }
       }
@@ -461,9 +472,10 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) miz_fast_kernel(const MizKA
     const int j = lane * K + i;
     if (j < nx) {
       const long long o = (long long)j * nmem + m;
-      a.Ei[o] = Ei[i]; a.Ew[o] = Ew[i]; a.h[o] = h[i]; a.D[o] = D[i]; a.phi[o] = phi[i]; a.T0[o] = T0[i];
-      bad = bad || !(fabs(Ei[i]) < 1e300) || !(fabs(Ew[i]) < 1e300) || !(fabs(h[i]) < 1e300) ||
-            !(fabs(D[i]) < 1e300) || !(fabs(phi[i]) < 1e300);
+      const double ei = EI(i), ew = EW(i), dd = DD(i);
+      a.Ei[o] = ei; a.Ew[o] = ew; a.h[o] = HH(i); a.D[o] = dd; a.phi[o] = phi[i]; a.T0[o] = T0[i];
+      bad = bad || !(fabs(ei) < 1e300) || !(fabs(ew) < 1e300) || !(fabs(HH(i)) < 1e300) ||
+            !(fabs(dd) < 1e300) || !(fabs(phi[i]) < 1e300);
     }
   }
   bad = __any_sync(kFull, bad);
@@ -478,7 +490,10 @@ template <int K, int MINB>
 int launch_k(const MizKArgs& a, cudaStream_t stream) {
   const long long blocks = (a.nmem + kWarps - 1) / kWarps;
   if (blocks > 0x7fffffffLL) { ebm_set_error("miz: too many members (%lld)", a.nmem); return EBM_ERR_INVALID; }
-  miz_fast_kernel<K, MINB><<<(unsigned)blocks, kWarps * 32, 0, stream>>>(a);
+  auto kern = miz_fast_kernel<K, MINB>;
+  EBM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Tabs<K>)));
+  EBM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  kern<<<(unsigned)blocks, kWarps * 32, sizeof(Tabs<K>), stream>>>(a);
   EBM_CUDA_TRY(cudaGetLastError());
   ebm_count_launch();
   return EBM_OK;
