@@ -101,10 +101,9 @@ struct Ctx {
   template <bool SLOW>
   __device__ __forceinline__ void sample(const ClassicKArgs& a, const int i, const double wj, const double En,
                                          const double T, const int season, const int ti, const int year,
-                                         double& dgT, double& dgE, double& dgA, double& dgX) {
-    const int eidx = (j0 + i) * MW + mi;
-    const double sEi = sumE[eidx] + En;
-    if (!SLOW) sumE[eidx] = sEi;
+                                         double& se, double& dgT, double& dgE, double& dgA, double& dgX) {
+    se += En;                                   // running annual sum of E of this cell (caller loads / stores it)
+    const double sEi = se;
     accT = fma(wj, T, accT);
     if (SLOW) {
       const int nx = a.nx, nt = a.nt;
@@ -133,8 +132,8 @@ struct Ctx {
           o[0] = vE; o[nx] = vT; o[2 * nx] = -vN * inv_Lf;
         }
       }
-      sumE[eidx] = (ti == nt) ? 0.0 : sEi;
       if (ti == nt) {
+        se = 0.0;
         if (cta_fields) { sumT[sidx] = 0.0; sumH[sidx] = 0.0; }
       }
     }
@@ -159,6 +158,9 @@ struct Ctx {
     for (int i = 0; i < K; ++i) has_ice = has_ice || is_neg(E[i]);
     if (!has_ice) {
       bool crossed = false;
+      double se[K];                                         // annual sums: loaded up front, stored after the loop, so
+#pragma unroll                                              // that the K cells overlap instead of serialising on smem
+      for (int i = 0; i < K; ++i) se[i] = sumE[(j0 + i) * MW + mi];
 #pragma unroll
       for (int i = 0; i < K; ++i) {
         const PhysTab p = phys[j0 + i];
@@ -171,8 +173,10 @@ struct Ctx {
         E[i] = En;
         Tg[i] = fma(dttau_cw, En, Tgo);
         crossed = crossed || is_neg(En);
-        sample<SLOW>(a, i, p.wts, En, T, season, ti, year, dgT, dgE, dgA, dgX);
+        sample<SLOW>(a, i, p.wts, En, T, season, ti, year, se[i], dgT, dgE, dgA, dgX);
       }
+#pragma unroll
+      for (int i = 0; i < K; ++i) sumE[(j0 + i) * MW + mi] = se[i];
       if (crossed) {                                        // freeze-up inside this step (rare): literal mask
 #pragma unroll
         for (int i = 0; i < K; ++i) rs.q(i) = 0.0;
@@ -223,7 +227,9 @@ struct Ctx {
         anymask = anymask || masked;
         E[i] = En;
         Tg[i] = masked ? rhs_m : (negn ? Tgo : rhs_w);
-        sample<SLOW>(a, i, p.wts, En, T, season, ti, year, dgT, dgE, dgA, dgX);
+        double se = sumE[(j0 + i) * MW + mi];
+        sample<SLOW>(a, i, p.wts, En, T, season, ti, year, se, dgT, dgE, dgA, dgX);
+        sumE[(j0 + i) * MW + mi] = se;
       }
     }
     if (SLOW && season == 2) dgT = accT * inv_nt;   // mean over the year of the hemispheric mean (linear)
@@ -568,6 +574,7 @@ int ebm_launch_classic_uniform(const ClassicKArgs& a, int variant, cudaStream_t 
     case 5: return launch_uniform<13, 8, 16, 255>(a, stream);         // band rows in registers: 2 CTAs per SM
     case 6: return launch_uniform<13, 8, 16, 128, true>(a, stream);   // band rows in shared memory, 128 registers (spills)
     case 7: return launch_uniform<13, 8, 16, 255, true>(a, stream);
+    case 8: return launch_uniform<7, 16, 16, 128, true>(a, stream);   // 16 bands of 7 cells, 8 warps per CTA, 2 CTAs per SM
     // default: band rows (pivots / spikes) in thread-private shared memory, 168 registers -> 3 CTAs (12 warps) per SM:
     // fastest measured at 65 536 members (826 k member-years/s vs 734 k with the rows in registers at 2 CTAs per SM)
     default: return launch_uniform<13, 8, 16, 168, true>(a, stream);
