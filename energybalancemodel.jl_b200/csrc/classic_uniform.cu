@@ -203,6 +203,9 @@ struct Ctx {
         }
       }
     } else {
+      double rv[K], se[K];                                  // carried reciprocals / annual sums: batched smem reads
+#pragma unroll
+      for (int i = 0; i < K; ++i) { rv[i] = rs.r(i); se[i] = sumE[(j0 + i) * MW + mi]; }
 #pragma unroll
       for (int i = 0; i < K; ++i) {
         const PhysTab p = phys[j0 + i];
@@ -211,7 +214,7 @@ struct Ctx {
         const bool ice = is_neg(Eo);
         const double alpha = ice ? ai : (is_zero(Eo) ? 0.0 : p.aw);                               //     :47
         const double C = fma(alpha, S, fma(cg_tau, Tgo, fmA));                                    //     :48
-        const double T0 = C * rs.r(i);                      // T0 = C/(M - kLf/E), 1/(M - kLf/E) carried     :50
+        const double T0 = C * rv[i];                        // T0 = C/(M - kLf/E), 1/(M - kLf/E) carried     :50
         const bool Cneg = C < 0.0;                          // for E < 0: M - kLf/E > 0, so T0 < 0 <=> C < 0
         const double T = ice ? (Cneg ? T0 : 0.0) : Eo * inv_cw;                                   //     :51
         const double En = fma(dt, fma(-M, T, C) + Fb, Eo);                                        //     :53
@@ -227,10 +230,10 @@ struct Ctx {
         anymask = anymask || masked;
         E[i] = En;
         Tg[i] = masked ? rhs_m : (negn ? Tgo : rhs_w);
-        double se = sumE[(j0 + i) * MW + mi];
-        sample<SLOW>(a, i, p.wts, En, T, season, ti, year, se, dgT, dgE, dgA, dgX);
-        sumE[(j0 + i) * MW + mi] = se;
+        sample<SLOW>(a, i, p.wts, En, T, season, ti, year, se[i], dgT, dgE, dgA, dgX);
       }
+#pragma unroll
+      for (int i = 0; i < K; ++i) sumE[(j0 + i) * MW + mi] = se[i];
     }
     if (SLOW && season == 2) dgT = accT * inv_nt;   // mean over the year of the hemispheric mean (linear)
     if (SLOW && ti == nt) accT = 0.0;
