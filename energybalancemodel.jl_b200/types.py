@@ -17,7 +17,7 @@ import numpy as np
 __all__ = [
     "Collection", "SpaceTime", "Forcing", "Solutions", "default_parval", "miz_paramset",
     "classic_paramset", "default_parameters", "CLASSIC_PAR_ORDER", "MIZ_PAR_ORDER",
-    "CLASSIC_VARS", "MIZ_VARS", "hemispheric_mean",
+    "CLASSIC_VARS", "MIZ_VARS", "hemispheric_mean", "annual_mean_forcing", "hysteresis_points",
 ]
 
 
@@ -170,6 +170,20 @@ def hemispheric_mean(vec, x) -> float:
     for i in range(len(x) - 1):
         acc += (vec[i] + vec[i + 1]) * (x[i + 1] - x[i]) / 2.0
     return acc
+
+
+def annual_mean_forcing(forcing: "Forcing", st: "SpaceTime", year: int) -> float:
+    """``annual_mean(forcing, st, year)`` (src/infrastructure.jl:546-547): mean of ``forcing.(year-1 .+ st.t)``."""
+    return float(np.mean([forcing((year - 1) + float(t)) for t in st.t]))
+
+
+def hysteresis_points(diag, season: int = 2):
+    """The points ``plot_seasonal`` draws (src/plot.jl:173-190) from the L0 diagnostics of an ensemble run:
+    x = hemispheric mean of the annual-mean temperature, y = ice-covered area ``2*pi*hemispheric_mean(phi)`` (MIZ) or
+    ``2*pi*hemispheric_mean(E < 0)`` (classic) of ``season`` (0 winter, 1 summer, 2 annual mean).
+    ``diag`` is ``[nmem, dur, 3, 4]``; returns two ``[nmem, dur]`` arrays."""
+    diag = np.asarray(diag)
+    return diag[:, :, 2, 0], diag[:, :, season, 2]
 
 
 class Solutions:

@@ -63,6 +63,24 @@ int main(void) {
     assert len(ebm.CLASSIC_PAR_ORDER) == _lib.CLASSIC_NPAR and len(ebm.MIZ_PAR_ORDER) == _lib.MIZ_NPAR
 
 
+def test_plain_c_consumer_links_and_fails_loudly_without_gpu(tmp_path):
+    """examples/c_abi_example.c: the header is usable from C11, the library links without torch/Python, and without
+    a device the compute call returns EBM_ERR_CUDA with a message (the example exits 0 in that case)."""
+    exe = str(tmp_path / "c_abi_example")
+    lib_dir = os.path.dirname(_lib.LIB_PATH)
+    r = subprocess.run(["gcc", "-std=c11", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "examples", "c_abi_example.c"), "-L", lib_dir, "-lebm_cuda", "-lm",
+                        f"-Wl,-rpath,{lib_dir}", "-o", exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "ebm_cuda" in out.stdout
+    if _lib.load().ebm_device_count() == 0:
+        assert "no CPU fallback" in out.stdout
+    else:
+        assert "annual mean" in out.stdout
+
+
 def _no_gpu():
     return _lib.load().ebm_device_count() == 0
 

@@ -47,6 +47,23 @@ def test_forcing_known_answers_and_errors():
         ebm.Forcing(0.0, 5.0, -5.0, (10, 10), (0.5, 0.5))        # cooling rate must be negative (:238)
 
 
+def test_forcing_annual_mean_and_hysteresis_points():
+    f = ebm.Forcing(0.0, 5.0, -5.0, (10, 10), (0.5, -0.5))
+    st = ebm.SpaceTime(100, 2000, 60)
+    assert ebm.annual_mean_forcing(f, st, 5) == 0.0                          # hold at base
+    assert abs(ebm.annual_mean_forcing(f, st, 11) - 0.25) < 1e-12           # first warming year: mean of 0..0.5
+    assert abs(ebm.annual_mean_forcing(f, st, 25) - 5.0) < 1e-12            # hold at peak
+    assert ebm.annual_mean_forcing(ebm.Forcing(1.5), st, 3) == 1.5
+    # plot_seasonal's x / y functions (src/plot.jl:173-190) on oracle fields == the L0 diagnostics layout
+    st1 = ebm.SpaceTime(100, 2000, 1)
+    o = oracle_classic(st1, [ebm.Forcing(0.0)], [ebm.default_parameters("Classic")], [cold_init(100)], seasonal=True)
+    d = oracle_diag_classic(o["seasonal"], st1.x)
+    x, y = ebm.hysteresis_points(d, season=0)
+    assert abs(x[0, 0] - ebm.hemispheric_mean(o["seasonal"][0, 0, 2, 1], st1.x)) < 1e-12
+    ice = (o["seasonal"][0, 0, 0, 0] < 0).astype(float)
+    assert abs(y[0, 0] - 2 * np.pi * ebm.hemispheric_mean(ice, st1.x)) < 1e-12
+
+
 def test_default_parameters():
     pm, pc = ebm.default_parameters("MIZ"), ebm.default_parameters("Classic")
     assert len(pm) == 22 and len(pc) == 16                       # src/EnergyBalanceModel.jl:29-41, infrastructure.jl:458
