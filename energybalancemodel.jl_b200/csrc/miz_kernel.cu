@@ -29,6 +29,7 @@
 // (DESIGN.md "MIZ sensitivity"), so long runs are compared through the literal kernel instead.
 #include <math.h>
 #include <stdlib.h>
+#include <type_traits>
 #include <string.h>
 
 #include "ebm_internal.cuh"
@@ -62,6 +63,13 @@ __device__ __forceinline__ double rcp_nr(double y) {
   r = fma(r, e, r);
   return r;
 }
+// c ? a : b as one SELP with both operands evaluated: the compiler otherwise branches around "expensive" operands,
+// which splits the unrolled per-cell code into scheduling regions and serialises the K cells of a lane
+__device__ __forceinline__ double sel(bool c, double a, double b) {
+  double r;
+  asm("{ .reg .pred p; setp.ne.s32 p, %3, 0; selp.f64 %0, %1, %2, p; }" : "=d"(r) : "d"(a), "d"(b), "r"((int)c));
+  return r;
+}
 // zero / sign tests on the integer pipe (the FP64 pipe is the bottleneck); +0 and -0 are both zero
 __device__ __forceinline__ bool is_zero(double v) { return ((__double2hiint(v) << 1) | __double2loint(v)) == 0; }
 // x / y with y an ordinary non-zero number (no denormal / huge denominators: DESIGN.md 4.3)
@@ -69,10 +77,10 @@ __device__ __forceinline__ double div_n(double x, double y) { return x * rcp_nr(
 // x / y with y zero or ordinary: IEEE results for y == +-0 (x/0 = +-Inf, 0/0 = NaN/0 = NaN), branch free
 __device__ __forceinline__ double div_z(double x, double y) {
   const bool z = is_zero(y);
-  const double q = x * rcp_nr(z ? 1.0 : y);
+  const double q = x * rcp_nr(sel(z, 1.0, y));
   const double inf = __hiloint2double(0x7ff00000 | ((__double2hiint(x) ^ __double2hiint(y)) & 0x80000000), 0);
   const double zq = (is_zero(x) || x != x) ? __longlong_as_double(0x7ff8000000000000LL) : inf;
-  return z ? zq : q;
+  return sel(z, zq, q);
 }
 
 template <int K>
@@ -281,8 +289,8 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) miz_fast_kernel(const MizKA
   double accT = 0.0, accE = 0.0, accP = 0.0;   // running hemispheric sums of the year (annual means are linear)
   unsigned icebits = 0u;
 
-  const bool sel = a.field_stride > 0 && (m % a.field_stride) == 0 && (a.seasonal != nullptr || a.raw != nullptr);
-  const long long msel = sel ? m / a.field_stride : 0;
+  const bool sel_m = a.field_stride > 0 && (m % a.field_stride) == 0 && (a.seasonal != nullptr || a.raw != nullptr);
+  const long long msel = sel_m ? m / a.field_stride : 0;
   long long iters_total = 0, fails_total = 0;
   const long long step_stop = a.step_limit > 0 ? (long long)a.step_limit : 0x7fffffffffffffffLL;
   const double tol = a.tol;
@@ -308,7 +316,7 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) miz_fast_kernel(const MizKA
         const int s = i * 32 + lane;
         const double om = 1 - phi[i];
         const double v = CST(Tm) + div_z(EW(i), om * CST(cw));                        // water_temp :30
-        const double tw = (v != v) ? 0.0 : v;                                  // :157
+        const double tw = sel(v != v, 0.0, v);                                 // :157
         TW(i) = tw;
         omTw[i] = om * tw;
         const double hp = is_zero(HH(i)) ? CST(hmin) : HH(i);                      // :51
@@ -328,11 +336,9 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) miz_fast_kernel(const MizKA
         for (int i = 0; i < K; ++i) {
           const double v = fma(kb[i], CST(Tm) - T0[i], c0[i] + res[i]);          // T0eq :39-43
           res[i] = -v;
-          if (lane * K + i < nx) {
-            const double av = fabs(v);
-            nan = nan || (av != av);
-            ok = ok && (av <= tol);
-          }
+          const double av = (lane * K + i < nx) ? fabs(v) : 0.0;
+          nan = nan || (av != av);
+          ok = ok && (av <= tol);
         }
         if (__all_sync(kFull, ok)) break;
         if (__any_sync(kFull, nan) || it >= maxit) { fail = 1; break; }
@@ -348,7 +354,7 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) miz_fast_kernel(const MizKA
           jd[i] = fma(-(l + u), g[i], -kb[i]);
           jl[i] = l * ((i == 0) ? gleft : g[i - 1]);
           ju[i] = u * ((i == K - 1) ? gright : g[i + 1]);
-          if (lane * K + i >= nx) res[i] = 0.0;
+          res[i] = (lane * K + i >= nx) ? 0.0 : res[i];
         }
         tridiag<K>(lane, jl, jd, ju, res);
         // The residual is piecewise linear: if the step leaves the active set [T0 < Tm] (where phi != 0) unchanged,
@@ -381,6 +387,9 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) miz_fast_kernel(const MizKA
       diffuse<K>(lo, up, lane, tb, dif);
 
       double dgT = 0.0, dgE = 0.0, dgP = 0.0, dgX = 2.0;
+      // two instantiations: the hot one (no sampling this step, no field output) is straight-line code
+      auto cells = [&](auto slow_tag) {
+      constexpr bool SLOW = decltype(slow_tag)::value;
 #pragma unroll
       for (int i = 0; i < K; ++i) {
         const int sidx = i * 32 + lane;
@@ -393,9 +402,9 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) miz_fast_kernel(const MizKA
         const double Fvi = c0[i] + common;                                            // :99-100 (ice)
         const double Fvw = fma(fma(-CST(a2), x2j, CST(a0)), S, fA) + common;                  // (water)
         const double wl = CST(m1) * (TW(i) - CST(Tm_m2));                                      // :71
-        const double rD = rcp_nr(noD ? 1.0 : Do);
-        const double n = noD ? 0.0 : pho * (rD * rD) * CST(inv_alpha);                     // num :84-85
-        const double Flat = noD ? 0.0 : (pho * ho) * (wl * CST(c_flat)) * rD;              // :104-105
+        const double rD = rcp_nr(sel(noD, 1.0, Do));
+        const double n = sel(noD, 0.0, pho * (rD * rD) * CST(inv_alpha));                     // num :84-85
+        const double Flat = sel(noD, 0.0, (pho * ho) * (wl * CST(c_flat)) * rD);              // :104-105
         const double rEi = fma(fma(pho, Fvi, Flat), dt, Eio);                         // :137,148,166
         const double rEw = fma(fma(om, Fvw, -Flat), dt, Ewo);                         // :138,148,167
         const double cEi = rEi > 0.0 ? 0.0 : rEi, cEw = rEw < 0.0 ? 0.0 : rEw;        // redistributeE :110-111
@@ -406,25 +415,25 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) miz_fast_kernel(const MizKA
         const double ring = CST(alpha) * n * fma(d2rl, d2rl, -Do * Do);                  // area_lead :91
         const double Al = (ring < om) ? ring : om;                                    // :92
         const double psiEw = psiEw_dt * ntd;                                          // psiEwdt / dt (:173)
-        const double Ql = one ? 0.0 : Al * rcp_nr(one ? 1.0 : om) * psiEw;            // split_psiEw :121-122
+        const double Ql = sel(one, 0.0, Al * rcp_nr(sel(one, 1.0, om)) * psiEw);            // split_psiEw :121-122
         const double Qp = psiEw - Ql;
         const double dn = -Qp * CST(c_dn);                                                 // :127,174
-        const double lat_grow = noh ? 0.0 : div_z(-Do, noh ? 1.0 : CST(twoLf) * ho * pho) * Ql;   // :142,144
+        const double lat_grow = sel(noh, 0.0, div_z(-Do, sel(noh, 1.0, CST(twoLf) * ho * pho)) * Ql);   // :142,144
         const double Dt = fma(CST(c_melt), wl, lat_grow) + CST(c_weld) * pho * (Do * Do * Do);  // :141-145
         const double rDn = fma(Dt, dt, Do);                                           // :175
         const double total = n + dn;
         const bool tz = is_zero(total);
-        const double rt = rcp_nr(tz ? 1.0 : total);
-        double Dn = tz ? 0.0 : fma(n, rDn, dn * CST(Dmin)) * rt;                          // average :131-132
+        const double rt = rcp_nr(sel(tz, 1.0, total));
+        double Dn = sel(tz, 0.0, fma(n, rDn, dn * CST(Dmin)) * rt);                          // average :131-132
         Dn = Dn > CST(Dmax) ? CST(Dmax) : (Dn < CST(Dmin) ? CST(Dmin) : Dn);                          // :177
-        if (is_zero(Ei_n)) Dn = 0.0;                                                   // :178
+        Dn = sel(is_zero(Ei_n), 0.0, Dn);                                                  // :178
         double rh = fma(-Fvi, CST(dt_Lf), ho);                                             // :139,179
         rh = rh < 0.0 ? 0.0 : rh;                                                     // :180
-        const double hn = tz ? 0.0 : fma(n, rh, dn * CST(hmin)) * rt;                     // :181
+        const double hn = sel(tz, 0.0, fma(n, rh, dn * CST(hmin)) * rt);                     // :181
         const bool hz = is_zero(hn);
-        double ph = hz ? 0.0 : div_n(-Ei_n, hz ? 1.0 : CST(Lf) * hn);                      // concentration :75-76
+        double ph = sel(hz, 0.0, div_n(-Ei_n, sel(hz, 1.0, CST(Lf) * hn)));                      // concentration :75-76
         if (ph > 1.0) ph = 1.0;                                                       // :77
-        if (hz) Ei_n = 0.0;                                                           // :185
+        Ei_n = sel(hz, 0.0, Ei_n);                                                          // :185
         const double omn = 1 - ph;
         const double En = fma(ph, Ei_n, omn * Ew_n);                                  // :186
         const double Tn = fma(Ti[i], ph, omn * TW(i));                                // :187
@@ -434,14 +443,15 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) miz_fast_kernel(const MizKA
         const bool real = lane * K + i < nx;
         const double wj = tabs.wts[sidx];
         accT = fma(wj, Tn, accT); accE = fma(wj, En, accE); accP = fma(wj, ph, accP);
-        if (ph > 0.0 && real) icebits |= 1u << i;
+        icebits |= (unsigned)(ph > 0.0 && real) << i;
+        if (SLOW) {
         if (season == 0 || season == 1) {
           dgT = fma(wj, Tn, dgT); dgE = fma(wj, En, dgE); dgP = fma(wj, ph, dgP);
           if (ph > 0.0 && real) dgX = fmin(dgX, xj);
         } else if (season == 2) {
           if (((icebits >> i) & 1u) != 0u) dgX = fmin(dgX, xj);
         }
-        if (sel && real) {
+        if (sel_m && real) {
           double v[EBM_MIZ_NVAR];
           v[EBM_MV_T] = Tn; v[EBM_MV_Ei] = Ei_n;
           v[EBM_MV_Ti] = is_zero(Ei_n) ? NAN : Ti[i];                                 // :193
@@ -450,7 +460,10 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) miz_fast_kernel(const MizKA
           v[EBM_MV_Tw] = (ph > 0.99) ? NAN : TW(i);                                   // :194
           store_cell(a, lane * K + i, msel, year, ti, season, v);
         }
+        }   // SLOW
       }
+      };    // cells
+      if (sel_m || season >= 0) cells(std::true_type{}); else cells(std::false_type{});
       if (season >= 0 && a.diag != nullptr) {
         if (season == 2) {   // annual means: mean over the year of the hemispheric means (linear)
           dgT = accT / ntd; dgE = accE / ntd; dgP = accP / ntd;
