@@ -80,7 +80,7 @@ struct RowStore {
   }
 };
 
-template <int K, int WB, int MW, bool QS_SMEM>
+template <int K, int WB, int MW, bool QS_SMEM, bool WARPM>
 struct Ctx {
   static constexpr int NXP = K * WB;
   // tables / scratch in shared memory
@@ -90,6 +90,9 @@ struct Ctx {
   double A, Fb, ai, cg_tau, M, kLf, inv_cw, dt, dt_tau, dttau_cw, dc, inv_nt, inv_Lf;
   // thread identity
   int band, mi, j0;
+  // index of cell i of this thread in the per-cell shared arrays (annual sums): [cell][member] when a warp holds
+  // 16 members of 2 bands; thread-private [i][thread] (conflict free) when a warp holds all bands of 4 members
+  __device__ __forceinline__ int cidx(int i) const { return WARPM ? (i * (WB * MW) + (int)threadIdx.x) : ((j0 + i) * MW + mi); }
   bool active, sel, cta_fields;
   long long m, msel;
   // state
@@ -108,7 +111,7 @@ struct Ctx {
     if (SLOW) {
       const int nx = a.nx, nt = a.nt;
       const int j = j0 + i;
-      const int sidx = j * MW + mi;
+      const int sidx = cidx(i);
       const double Eneg = is_neg(En) ? En : 0.0;
       if (cta_fields) { sumT[sidx] += T; sumH[sidx] += Eneg; }
       const bool rawstep = sel && a.raw != nullptr && (!a.lastonly || year == a.dur - 1);
@@ -160,7 +163,7 @@ struct Ctx {
       bool crossed = false;
       double se[K];                                         // annual sums: loaded up front, stored after the loop, so
 #pragma unroll                                              // that the K cells overlap instead of serialising on smem
-      for (int i = 0; i < K; ++i) se[i] = sumE[(j0 + i) * MW + mi];
+      for (int i = 0; i < K; ++i) se[i] = sumE[cidx(i)];
 #pragma unroll
       for (int i = 0; i < K; ++i) {
         const PhysTab p = phys[j0 + i];
@@ -176,7 +179,7 @@ struct Ctx {
         sample<SLOW>(a, i, p.wts, En, T, season, ti, year, se[i], dgT, dgE, dgA, dgX);
       }
 #pragma unroll
-      for (int i = 0; i < K; ++i) sumE[(j0 + i) * MW + mi] = se[i];
+      for (int i = 0; i < K; ++i) sumE[cidx(i)] = se[i];
       if (crossed) {                                        // freeze-up inside this step (rare): literal mask
 #pragma unroll
         for (int i = 0; i < K; ++i) rs.q(i) = 0.0;
@@ -205,7 +208,7 @@ struct Ctx {
     } else {
       double rv[K], se[K];                                  // carried reciprocals / annual sums: batched smem reads
 #pragma unroll
-      for (int i = 0; i < K; ++i) { rv[i] = rs.r(i); se[i] = sumE[(j0 + i) * MW + mi]; }
+      for (int i = 0; i < K; ++i) { rv[i] = rs.r(i); se[i] = sumE[cidx(i)]; }
 #pragma unroll
       for (int i = 0; i < K; ++i) {
         const PhysTab p = phys[j0 + i];
@@ -233,14 +236,14 @@ struct Ctx {
         sample<SLOW>(a, i, p.wts, En, T, season, ti, year, se[i], dgT, dgE, dgA, dgX);
       }
 #pragma unroll
-      for (int i = 0; i < K; ++i) sumE[(j0 + i) * MW + mi] = se[i];
+      for (int i = 0; i < K; ++i) sumE[cidx(i)] = se[i];
     }
     if (SLOW && season == 2) dgT = accT * inv_nt;   // mean over the year of the hemispheric mean (linear)
     if (SLOW && ti == nt) accT = 0.0;
 
     PHASE_MARK(0);   // physics
     // ---- local elimination  x_i + q_i x_{i+1} + s_i xL = y_i  and reduction of row 0 to (al, be, ga)
-    double* f6 = iface + (band * 6) * MW + mi;
+    double i_sl, i_ql, i_yl, i_al, i_be, i_ga;   // this band's interface row (last row + row 0 reduced)
     if (!anymask) {
       // member-independent pivots (precomputed): only the right-hand side is eliminated
       double yprev = 0.0;
@@ -254,8 +257,8 @@ struct Ctx {
 #pragma unroll
       for (int i = K - 3; i >= 0; --i) al = fma(-elim[j0 + i].q, al, Tg[i]);
       const ElimTab el = elim[j0 + K - 1];
-      f6[0 * MW] = el.s; f6[1 * MW] = el.q; f6[2 * MW] = Tg[K - 1];
-      f6[3 * MW] = al; f6[4 * MW] = bandc[2 * band]; f6[5 * MW] = bandc[2 * band + 1];
+      i_sl = el.s; i_ql = el.q; i_yl = Tg[K - 1];
+      i_al = al; i_be = bandc[2 * band]; i_ga = bandc[2 * band + 1];
     } else {
       // pivots in determinant form: P_i = w_0 ... w_i obeys P_i = d_i P_{i-1} - (a_i c_{i-1}) P_{i-2}, one dependent FMA
       // per row; the K reciprocals 1/w_i = P_{i-1}/P_i are then independent of each other (|w| ~ 50..250: no overflow)
@@ -286,8 +289,57 @@ struct Ctx {
         be = fma(-rs.q(i), be, rs.s(i));
         ga = -rs.q(i) * ga;
       }
-      f6[0 * MW] = rs.s(K - 1); f6[1 * MW] = rs.q(K - 1); f6[2 * MW] = Tg[K - 1];
-      f6[3 * MW] = al; f6[4 * MW] = be; f6[5 * MW] = ga;
+      i_sl = rs.s(K - 1); i_ql = rs.q(K - 1); i_yl = Tg[K - 1];
+      i_al = al; i_be = be; i_ga = ga;
+    }
+    double xL, xn;
+    if constexpr (WARPM) {
+      // ---- all WB bands of a member sit in one warp (lane = band * MPW + member): the interface system
+      //   A z_{b-1} + z_b + C z_{b+1} = R   is solved by parallel cyclic reduction over shuffles; no CTA barrier
+      constexpr int MPW = 32 / WB;                           // members per warp
+      constexpr unsigned kFull = 0xffffffffu;
+      const double nal = __shfl_down_sync(kFull, i_al, MPW), nbe = __shfl_down_sync(kFull, i_be, MPW);
+      const double nga = __shfl_down_sync(kFull, i_ga, MPW);
+      const double ql = (band == WB - 1) ? 0.0 : i_ql;
+      double A = (band == 0) ? 0.0 : i_sl;
+      double C = -ql * nga;
+      double R = fma(-ql, nal, i_yl);
+      {
+        const double ib = fast_rcp(fma(-ql, nbe, 1.0));
+        A *= ib; C *= ib; R *= ib;
+      }
+#pragma unroll
+      for (int st = 1; st < WB; st <<= 1) {
+        const double Au = __shfl_up_sync(kFull, A, st * MPW), Cu = __shfl_up_sync(kFull, C, st * MPW);
+        const double Ru = __shfl_up_sync(kFull, R, st * MPW);
+        const double Ad = __shfl_down_sync(kFull, A, st * MPW), Cd = __shfl_down_sync(kFull, C, st * MPW);
+        const double Rd = __shfl_down_sync(kFull, R, st * MPW);
+        const double a_ = (band >= st) ? A : 0.0, c_ = (band + st < WB) ? C : 0.0;
+        const double ib = fast_rcp(fma(-a_, Cu, fma(-c_, Ad, 1.0)));
+        const double Rn = fma(-a_, Ru, fma(-c_, Rd, R));
+        A = -(a_ * Au) * ib;
+        C = -(c_ * Cd) * ib;
+        R = Rn * ib;
+      }
+      xn = R;
+      const double zup = __shfl_up_sync(kFull, R, MPW);
+      xL = (band > 0) ? zup : 0.0;
+      if (SLOW && season >= 0) {                             // diagnostics: reduce the member's WB band partials
+#pragma unroll
+        for (int o = MPW; o < 32; o <<= 1) {
+          dgT += __shfl_xor_sync(kFull, dgT, o); dgE += __shfl_xor_sync(kFull, dgE, o);
+          dgA += __shfl_xor_sync(kFull, dgA, o); dgX = fmin(dgX, __shfl_xor_sync(kFull, dgX, o));
+        }
+        if (band == 0 && a.diag != nullptr && active) {
+          double* o = a.diag + ((m * a.dur + year) * 3 + season) * 4;
+          o[0] = dgT; o[1] = dgE; o[2] = kTwoPi * dgA; o[3] = (dgX > 1.5) ? 1.0 : dgX;
+        }
+      }
+      PHASE_MARK(3);
+    } else {
+    {
+    double* f6 = iface + (band * 6) * MW + mi;
+    f6[0 * MW] = i_sl; f6[1 * MW] = i_ql; f6[2 * MW] = i_yl; f6[3 * MW] = i_al; f6[4 * MW] = i_be; f6[5 * MW] = i_ga;
     }
     if (SLOW && season >= 0) {
       double* r4 = red + (band * 4) * MW + mi;
@@ -352,8 +404,9 @@ struct Ctx {
     __syncthreads();
     PHASE_MARK(4);   // barrier 2 wait
     // ---- back substitution with the true neighbours
-    const double xL = (band > 0) ? zs[(band - 1) * MW + mi] : 0.0;
-    double xn = zs[band * MW + mi];
+    xL = (band > 0) ? zs[(band - 1) * MW + mi] : 0.0;
+    xn = zs[band * MW + mi];
+    }
     Tg[K - 1] = xn;
     if (!anymask) {
 #pragma unroll
@@ -381,17 +434,20 @@ constexpr size_t uniform_smem_bytes(bool fields) {
                            (QS_SMEM ? (size_t)3 * K * WB * MW : 0));
 }
 
-template <int K, int WB, int MW, int MAXR, bool QS_SMEM>
+template <int K, int WB, int MW, int MAXR, bool QS_SMEM, bool WARPM>
 __global__ void __maxnreg__(MAXR) classic_uniform_kernel(const ClassicKArgs a) {
   static_assert(MW == 16, "warp 0 = two lanes per member (full-warp shuffles)");
+  static_assert(!WARPM || (32 % WB == 0 && QS_SMEM), "member-in-warp mapping: WB bands x 32/WB members per warp");
   static_assert(WB % 2 == 0 && (WB * MW) % 32 == 0, "whole warps, even band count");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int BPW = 32 / MW;
   constexpr int NXP = K * WB;
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
-  const int mi = lane & (MW - 1);
-  const int band = warp * BPW + lane / MW;
+  // warp = BPW bands x MW members (interface through shared memory and two CTA barriers), or, WARPM, warp = all WB
+  // bands x 32/WB members (interface through shuffles, no barrier in the time loop)
+  const int mi = WARPM ? (warp * (32 / WB) + (lane & (32 / WB - 1))) : (lane & (MW - 1));
+  const int band = WARPM ? (lane / (32 / WB)) : (warp * BPW + lane / MW);
   const long long nmem = a.nmem;
   const long long m_first = (long long)blockIdx.x * MW;
   const long long m_raw = m_first + mi;
@@ -464,7 +520,7 @@ __global__ void __maxnreg__(MAXR) classic_uniform_kernel(const ClassicKArgs a) {
     bandc[2 * b] = be; bandc[2 * b + 1] = ga;
   }
 
-  Ctx<K, WB, MW, QS_SMEM> cx;
+  Ctx<K, WB, MW, QS_SMEM, WARPM> cx;
   cx.rs.base = qsm + tid;
   cx.rs.stride = WB * MW;
   cx.phys = phys; cx.elim = elim; cx.coef = coef; cx.bandc = bandc;
@@ -485,9 +541,9 @@ __global__ void __maxnreg__(MAXR) classic_uniform_kernel(const ClassicKArgs a) {
     const bool v = j < nx;
     cx.E[i] = v ? a.E[(long long)j * nmem + m] : 1.0;     // pad cells: decoupled open-water rows
     cx.Tg[i] = v ? a.Tg[(long long)j * nmem + m] : 0.0;
-    sumE[j * MW + mi] = 0.0;
+    sumE[cx.cidx(i)] = 0.0;
     cx.rs.r(i) = cx.E[i] * fast_rcp(fma(cx.M, cx.E[i], -cx.kLf));   // same expression as in the step: r is a pure function of E
-    if (cx.cta_fields) { sumT[j * MW + mi] = 0.0; sumH[j * MW + mi] = 0.0; }
+    if (cx.cta_fields) { sumT[cx.cidx(i)] = 0.0; sumH[cx.cidx(i)] = 0.0; }
   }
   // Forcing{true}: base == peak == cool, all breakpoints 0 -> the call is the constant `base`
   const double fbase = fr[0 * MW + mi];
@@ -529,7 +585,7 @@ __global__ void __maxnreg__(MAXR) classic_uniform_kernel(const ClassicKArgs a) {
   if (bad && a.flags != nullptr) atomicOr(a.flags + m, 1);
 }
 
-template <int K, int WB, int MW, int MAXR, bool QS_SMEM = false>
+template <int K, int WB, int MW, int MAXR, bool QS_SMEM = false, bool WARPM = false>
 int launch_uniform(const ClassicKArgs& a, cudaStream_t stream) {
   if (a.nx > K * WB) {
     ebm_set_error("classic_uniform: nx=%d exceeds %d bands of %d cells", a.nx, WB, K);
@@ -537,7 +593,7 @@ int launch_uniform(const ClassicKArgs& a, cudaStream_t stream) {
   }
   const bool fields = a.seasonal != nullptr && a.field_stride > 0;
   const size_t smem = uniform_smem_bytes<K, WB, MW, QS_SMEM>(fields);
-  auto kern = classic_uniform_kernel<K, WB, MW, MAXR, QS_SMEM>;
+  auto kern = classic_uniform_kernel<K, WB, MW, MAXR, QS_SMEM, WARPM>;
   EBM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // leave room for several CTAs per SM: ask for the largest shared-memory carve-out (L1 is hardly used)
   EBM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -578,6 +634,8 @@ int ebm_launch_classic_uniform(const ClassicKArgs& a, int variant, cudaStream_t 
     case 6: return launch_uniform<13, 8, 16, 128, true>(a, stream);   // band rows in shared memory, 128 registers (spills)
     case 7: return launch_uniform<13, 8, 16, 255, true>(a, stream);
     case 8: return launch_uniform<7, 16, 16, 128, true>(a, stream);   // 16 bands of 7 cells, 8 warps per CTA, 2 CTAs per SM
+    case 9: return launch_uniform<13, 8, 16, 168, true, true>(a, stream);   // member-in-warp mapping, no CTA barrier
+    case 10: return launch_uniform<13, 8, 16, 255, true, true>(a, stream);
     // default: band rows (pivots / spikes) in thread-private shared memory, 168 registers -> 3 CTAs (12 warps) per SM:
     // fastest measured at 65 536 members (826 k member-years/s vs 734 k with the rows in registers at 2 CTAs per SM)
     default: return launch_uniform<13, 8, 16, 168, true>(a, stream);
