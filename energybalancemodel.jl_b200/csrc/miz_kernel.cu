@@ -87,13 +87,14 @@ template <int K>
 struct Tabs {   // per CTA, [i][lane] for cell j = lane*K + i
   double x[K * 32], x2[K * 32], wts[K * 32];
   double lo[kWarps][K * 32], up[kWarps][K * 32];   // member's D times the stencil coefficient towards j-1 / j+1
-  double cst[kWarps][48];                          // member constants (warp-uniform: broadcast loads, not registers)
-  double cold[kWarps][5 * K * 32];                 // Ei, Ew, D, h, Tw: touched once or twice per step -> thread-private smem
+  double cst[kWarps][56];                          // member constants (warp-uniform: broadcast loads, not registers)
+  double cold[kWarps][7 * K * 32];                 // Ei, Ew, D, h, Tw, 1/(1-phi), 1/hp: touched once or twice per step
 };
 
 // indices into Tabs::cst
 enum { cA, cB, ccw, cS0, cS1, cS2, ca0, ca2, cai, cFb, ck, cLf, cTm, cm1, calpha, cDmin, cDmax, chmin,
-       cTm_m2, cinv_alpha, cc_dn, cc_melt, cc_weld, cc_flat, cdt_Lf, ctwoLf, ctworl, cF0, cNCST = cF0 + EBM_NFORCING };
+       cTm_m2, cinv_alpha, cc_dn, cc_melt, cc_weld, cc_flat, cdt_Lf, ctwoLf, ctworl,
+       cinv_cw, cinv_Lf, cinv_hmin, cc_r1, cc_r2, cc_wl0, ccBF, cF0, cNCST = cF0 + EBM_NFORCING };
 
 // ---- D nabla^2 of a profile held K cells per lane:  up*(T[j+1]-T[j]) - lo*(T[j]-T[j-1])  (infrastructure.jl:495-527)
 template <int K>
@@ -151,6 +152,8 @@ __device__ __forceinline__ void tridiag(int lane, const double (&jl)[K], const d
   // parallel cyclic reduction, rows kept normalised (B = 1); out-of-range neighbours are identity rows
 #pragma unroll
   for (int st = 1; st < 32; st <<= 1) {
+    // couplings shrink quadratically (products of 2^k original ones): the last steps are usually no-ops
+    if (st >= 8 && !__any_sync(kFull, fabs(A) + fabs(C) > 1e-19)) break;
     const double Au = __shfl_up_sync(kFull, A, st), Cu = __shfl_up_sync(kFull, C, st), Ru = __shfl_up_sync(kFull, R, st);
     const double Ad = __shfl_down_sync(kFull, A, st), Cd = __shfl_down_sync(kFull, C, st), Rd = __shfl_down_sync(kFull, R, st);
     const double a_ = (lane >= st) ? A : 0.0, c_ = (lane + st < 32) ? C : 0.0;
@@ -260,6 +263,10 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) miz_fast_kernel(const MizKA
     c[cdt_Lf] = dt / pLf;                                                    // :139
     c[ctwoLf] = 2 * pLf;
     c[ctworl] = 2.0 * prl;
+    c[cinv_cw] = 1.0 / c[ccw]; c[cinv_Lf] = 1.0 / pLf; c[cinv_hmin] = rcp_nr(phmin);
+    c[cc_r1] = 4.0 * prl; c[cc_r2] = 4.0 * prl * prl;                        // (D + 2 rl)^2 - D^2 = 4 rl D + 4 rl^2  (:91)
+    c[cc_wl0] = -c[cm1] * c[cTm_m2];                                         // wlat = m1*Tw - m1*Tm^m2       (:71)
+    c[ccBF] = c[cB] * pTm + c[cFb];
     for (int r = 0; r < EBM_NFORCING; ++r) c[cF0 + r] = a.forc[(long long)r * nmem + m];
   }
   __syncwarp();
@@ -277,6 +284,8 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) miz_fast_kernel(const MizKA
 #define DD(i) cold[(2 * K + (i)) * 32]
 #define HH(i) cold[(3 * K + (i)) * 32]
 #define TW(i) cold[(4 * K + (i)) * 32]
+#define ROM(i) cold[(5 * K + (i)) * 32]   /* 1/(1-phi) of this step (1 where phi == 1) */
+#define RHP(i) cold[(6 * K + (i)) * 32]   /* 1/hp, hp = h or hmin where h == 0: carried from the step that made h */
   double phi[K], T0[K];
 #pragma unroll
   for (int i = 0; i < K; ++i) {
@@ -285,6 +294,8 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) miz_fast_kernel(const MizKA
     const long long o = (long long)j * nmem + m;
     EI(i) = v ? a.Ei[o] : 0.0; EW(i) = v ? a.Ew[o] : 0.0; HH(i) = v ? a.h[o] : 0.0;
     DD(i) = v ? a.D[o] : 0.0; phi[i] = v ? a.phi[o] : 0.0; T0[i] = v ? a.T0[o] : 0.0;
+    const double h0 = HH(i);
+    RHP(i) = sel(is_zero(h0), cst[cinv_hmin], rcp_nr(sel(is_zero(h0), 1.0, h0)));   // same expression as in the step
   }
   double accT = 0.0, accE = 0.0, accP = 0.0;   // running hemispheric sums of the year (annual means are linear)
   unsigned icebits = 0u;
@@ -315,12 +326,18 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) miz_fast_kernel(const MizKA
       for (int i = 0; i < K; ++i) {
         const int s = i * 32 + lane;
         const double om = 1 - phi[i];
-        const double v = CST(Tm) + div_z(EW(i), om * CST(cw));                        // water_temp :30
+        const bool one = phi[i] == 1.0;
+        const double r_om = rcp_nr(sel(one, 1.0, om));                         // shared by water_temp and split_psiEw
+        ROM(i) = r_om;
+        const double ew = EW(i);
+        // Ew / ((1-phi) cw) (:30); phi == 1: the IEEE quotient by +0 (NaN for Ew == 0 or NaN, else +-Inf)
+        const double qz = (is_zero(ew) || ew != ew) ? __longlong_as_double(0x7ff8000000000000LL)
+                                                     : __hiloint2double(0x7ff00000 | (__double2hiint(ew) & 0x80000000), 0);
+        const double v = CST(Tm) + sel(one, qz, ew * r_om * CST(inv_cw));
         const double tw = sel(v != v, 0.0, v);                                 // :157
         TW(i) = tw;
         omTw[i] = om * tw;
-        const double hp = is_zero(HH(i)) ? CST(hmin) : HH(i);                      // :51
-        kb[i] = div_n(CST(k), hp) + CST(B);                                           // k/hp + B
+        kb[i] = fma(CST(k), RHP(i), CST(B));                                   // k/hp + B, hp = h or hmin (:51)
         const double S = fma(-CST(S2), tabs.x2[s], fma(-S1c, tabs.x[s], CST(S0)));   // :11
         c0[i] = fma(CST(ai), S, fA);                                             // ai*S - A + f
       }
@@ -337,7 +354,7 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) miz_fast_kernel(const MizKA
           const double v = fma(kb[i], CST(Tm) - T0[i], c0[i] + res[i]);          // T0eq :39-43
           res[i] = -v;
           const double av = (lane * K + i < nx) ? fabs(v) : 0.0;
-          nan = nan || (av != av);
+          nan = nan || ((__double2hiint(av) & 0x7ff00000) == 0x7ff00000);   // NaN or Inf residual
           ok = ok && (av <= tol);
         }
         if (__all_sync(kFull, ok)) break;
@@ -398,12 +415,13 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) miz_fast_kernel(const MizKA
         const double om = 1 - pho;
         const bool noD = is_zero(Do), noh = is_zero(ho), one = pho == 1.0;
         const double S = fma(-CST(S2), x2j, fma(-S1c, xj, CST(S0)));
-        const double common = (dif[i] - CST(B) * (tb[i] - CST(Tm))) + CST(Fb);                    // -(A + B(Tb-Tm)) + diffusion + Fb (+ fA below)
+        const double common = fma(-CST(B), tb[i], dif[i]) + CST(cBF);                    // -(A + B(Tb-Tm)) + diffusion + Fb (+ fA below)
         const double Fvi = c0[i] + common;                                            // :99-100 (ice)
         const double Fvw = fma(fma(-CST(a2), x2j, CST(a0)), S, fA) + common;                  // (water)
-        const double wl = CST(m1) * (TW(i) - CST(Tm_m2));                                      // :71
+        const double wl = fma(CST(m1), TW(i), CST(c_wl0));                                      // :71
         const double rD = rcp_nr(sel(noD, 1.0, Do));
-        const double n = sel(noD, 0.0, pho * (rD * rD) * CST(inv_alpha));                     // num :84-85
+        const double an = sel(noD, 0.0, pho * (rD * rD));                              // alpha * n
+        const double n = an * CST(inv_alpha);                                            // num :84-85
         const double Flat = sel(noD, 0.0, (pho * ho) * (wl * CST(c_flat)) * rD);              // :104-105
         const double rEi = fma(fma(pho, Fvi, Flat), dt, Eio);                         // :137,148,166
         const double rEw = fma(fma(om, Fvw, -Flat), dt, Ewo);                         // :138,148,167
@@ -411,11 +429,10 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) miz_fast_kernel(const MizKA
         const double psiEw_dt = rEw - cEw;
         double Ei_n = cEi + psiEw_dt;
         const double Ew_n = cEw + (rEi - cEi);
-        const double d2rl = Do + CST(tworl);
-        const double ring = CST(alpha) * n * fma(d2rl, d2rl, -Do * Do);                  // area_lead :91
+        const double ring = an * fma(CST(c_r1), Do, CST(c_r2));                          // area_lead :91
         const double Al = (ring < om) ? ring : om;                                    // :92
         const double psiEw = psiEw_dt * ntd;                                          // psiEwdt / dt (:173)
-        const double Ql = sel(one, 0.0, Al * rcp_nr(sel(one, 1.0, om)) * psiEw);            // split_psiEw :121-122
+        const double Ql = sel(one, 0.0, Al * ROM(i) * psiEw);            // split_psiEw :121-122
         const double Qp = psiEw - Ql;
         const double dn = -Qp * CST(c_dn);                                                 // :127,174
         const double lat_grow = sel(noh, 0.0, div_z(-Do, sel(noh, 1.0, CST(twoLf) * ho * pho)) * Ql);   // :142,144
@@ -431,7 +448,9 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) miz_fast_kernel(const MizKA
         rh = rh < 0.0 ? 0.0 : rh;                                                     // :180
         const double hn = sel(tz, 0.0, fma(n, rh, dn * CST(hmin)) * rt);                     // :181
         const bool hz = is_zero(hn);
-        double ph = sel(hz, 0.0, div_n(-Ei_n, sel(hz, 1.0, CST(Lf) * hn)));                      // concentration :75-76
+        const double r_hn = rcp_nr(sel(hz, 1.0, hn));
+        RHP(i) = sel(hz, CST(inv_hmin), r_hn);                                           // next step's 1/hp (:51)
+        double ph = sel(hz, 0.0, -Ei_n * r_hn * CST(inv_Lf));                              // concentration :75-76
         if (ph > 1.0) ph = 1.0;                                                       // :77
         Ei_n = sel(hz, 0.0, Ei_n);                                                          // :185
         const double omn = 1 - ph;
