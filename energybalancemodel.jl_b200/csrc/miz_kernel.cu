@@ -65,11 +65,15 @@ __device__ __forceinline__ double rcp_nr(double y) {
 }
 // c ? a : b as one SELP with both operands evaluated: the compiler otherwise branches around "expensive" operands,
 // which splits the unrolled per-cell code into scheduling regions and serialises the K cells of a lane
-__device__ __forceinline__ double sel(bool c, double a, double b) {
-  double r;
-  asm("{ .reg .pred p; setp.ne.s32 p, %3, 0; selp.f64 %0, %1, %2, p; }" : "=d"(r) : "d"(a), "d"(b), "r"((int)c));
-  return r;
+__device__ __forceinline__ double keep(double v) {
+  // an empty asm "touches" the operand: it must be computed before the select and cannot be sunk into a conditional
+  // arm; the select itself stays a plain predicate select (2 FSEL, no predicate materialisation)
+  asm("" : "+d"(v));
+  return v;
 }
+__device__ __forceinline__ double sel(bool c, double a, double b) { return c ? keep(a) : keep(b); }
+__device__ __forceinline__ double sel0(bool c, double b) { return c ? 0.0 : keep(b); }   // c ? 0 : b
+__device__ __forceinline__ double sel1(bool c, double b) { return c ? 1.0 : keep(b); }   // c ? 1 : b
 // zero / sign tests on the integer pipe (the FP64 pipe is the bottleneck); +0 and -0 are both zero
 __device__ __forceinline__ bool is_zero(double v) { return ((__double2hiint(v) << 1) | __double2loint(v)) == 0; }
 // x / y with y an ordinary non-zero number (no denormal / huge denominators: DESIGN.md 4.3)
@@ -77,7 +81,7 @@ __device__ __forceinline__ double div_n(double x, double y) { return x * rcp_nr(
 // x / y with y zero or ordinary: IEEE results for y == +-0 (x/0 = +-Inf, 0/0 = NaN/0 = NaN), branch free
 __device__ __forceinline__ double div_z(double x, double y) {
   const bool z = is_zero(y);
-  const double q = x * rcp_nr(sel(z, 1.0, y));
+  const double q = x * rcp_nr(sel1(z, y));
   const double inf = __hiloint2double(0x7ff00000 | ((__double2hiint(x) ^ __double2hiint(y)) & 0x80000000), 0);
   const double zq = (is_zero(x) || x != x) ? __longlong_as_double(0x7ff8000000000000LL) : inf;
   return sel(z, zq, q);
@@ -295,7 +299,7 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) miz_fast_kernel(const MizKA
     EI(i) = v ? a.Ei[o] : 0.0; EW(i) = v ? a.Ew[o] : 0.0; HH(i) = v ? a.h[o] : 0.0;
     DD(i) = v ? a.D[o] : 0.0; phi[i] = v ? a.phi[o] : 0.0; T0[i] = v ? a.T0[o] : 0.0;
     const double h0 = HH(i);
-    RHP(i) = sel(is_zero(h0), cst[cinv_hmin], rcp_nr(sel(is_zero(h0), 1.0, h0)));   // same expression as in the step
+    RHP(i) = sel(is_zero(h0), cst[cinv_hmin], rcp_nr(sel1(is_zero(h0), h0)));   // same expression as in the step
   }
   double accT = 0.0, accE = 0.0, accP = 0.0;   // running hemispheric sums of the year (annual means are linear)
   unsigned icebits = 0u;
@@ -327,14 +331,14 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) miz_fast_kernel(const MizKA
         const int s = i * 32 + lane;
         const double om = 1 - phi[i];
         const bool one = phi[i] == 1.0;
-        const double r_om = rcp_nr(sel(one, 1.0, om));                         // shared by water_temp and split_psiEw
+        const double r_om = rcp_nr(sel1(one, om));                         // shared by water_temp and split_psiEw
         ROM(i) = r_om;
         const double ew = EW(i);
         // Ew / ((1-phi) cw) (:30); phi == 1: the IEEE quotient by +0 (NaN for Ew == 0 or NaN, else +-Inf)
         const double qz = (is_zero(ew) || ew != ew) ? __longlong_as_double(0x7ff8000000000000LL)
                                                      : __hiloint2double(0x7ff00000 | (__double2hiint(ew) & 0x80000000), 0);
         const double v = CST(Tm) + sel(one, qz, ew * r_om * CST(inv_cw));
-        const double tw = sel(v != v, 0.0, v);                                 // :157
+        const double tw = sel0(v != v, v);                                 // :157
         TW(i) = tw;
         omTw[i] = om * tw;
         kb[i] = fma(CST(k), RHP(i), CST(B));                                   // k/hp + B, hp = h or hmin (:51)
@@ -419,10 +423,10 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) miz_fast_kernel(const MizKA
         const double Fvi = c0[i] + common;                                            // :99-100 (ice)
         const double Fvw = fma(fma(-CST(a2), x2j, CST(a0)), S, fA) + common;                  // (water)
         const double wl = fma(CST(m1), TW(i), CST(c_wl0));                                      // :71
-        const double rD = rcp_nr(sel(noD, 1.0, Do));
-        const double an = sel(noD, 0.0, pho * (rD * rD));                              // alpha * n
+        const double rD = rcp_nr(sel1(noD, Do));
+        const double an = sel0(noD, pho * (rD * rD));                              // alpha * n
         const double n = an * CST(inv_alpha);                                            // num :84-85
-        const double Flat = sel(noD, 0.0, (pho * ho) * (wl * CST(c_flat)) * rD);              // :104-105
+        const double Flat = sel0(noD, (pho * ho) * (wl * CST(c_flat)) * rD);              // :104-105
         const double rEi = fma(fma(pho, Fvi, Flat), dt, Eio);                         // :137,148,166
         const double rEw = fma(fma(om, Fvw, -Flat), dt, Ewo);                         // :138,148,167
         const double cEi = rEi > 0.0 ? 0.0 : rEi, cEw = rEw < 0.0 ? 0.0 : rEw;        // redistributeE :110-111
@@ -432,27 +436,27 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) miz_fast_kernel(const MizKA
         const double ring = an * fma(CST(c_r1), Do, CST(c_r2));                          // area_lead :91
         const double Al = (ring < om) ? ring : om;                                    // :92
         const double psiEw = psiEw_dt * ntd;                                          // psiEwdt / dt (:173)
-        const double Ql = sel(one, 0.0, Al * ROM(i) * psiEw);            // split_psiEw :121-122
+        const double Ql = sel0(one, Al * ROM(i) * psiEw);            // split_psiEw :121-122
         const double Qp = psiEw - Ql;
         const double dn = -Qp * CST(c_dn);                                                 // :127,174
-        const double lat_grow = sel(noh, 0.0, div_z(-Do, sel(noh, 1.0, CST(twoLf) * ho * pho)) * Ql);   // :142,144
+        const double lat_grow = sel0(noh, div_z(-Do, sel1(noh, CST(twoLf) * ho * pho)) * Ql);   // :142,144
         const double Dt = fma(CST(c_melt), wl, lat_grow) + CST(c_weld) * pho * (Do * Do * Do);  // :141-145
         const double rDn = fma(Dt, dt, Do);                                           // :175
         const double total = n + dn;
         const bool tz = is_zero(total);
-        const double rt = rcp_nr(sel(tz, 1.0, total));
-        double Dn = sel(tz, 0.0, fma(n, rDn, dn * CST(Dmin)) * rt);                          // average :131-132
+        const double rt = rcp_nr(sel1(tz, total));
+        double Dn = sel0(tz, fma(n, rDn, dn * CST(Dmin)) * rt);                          // average :131-132
         Dn = Dn > CST(Dmax) ? CST(Dmax) : (Dn < CST(Dmin) ? CST(Dmin) : Dn);                          // :177
-        Dn = sel(is_zero(Ei_n), 0.0, Dn);                                                  // :178
+        Dn = sel0(is_zero(Ei_n), Dn);                                                  // :178
         double rh = fma(-Fvi, CST(dt_Lf), ho);                                             // :139,179
         rh = rh < 0.0 ? 0.0 : rh;                                                     // :180
-        const double hn = sel(tz, 0.0, fma(n, rh, dn * CST(hmin)) * rt);                     // :181
+        const double hn = sel0(tz, fma(n, rh, dn * CST(hmin)) * rt);                     // :181
         const bool hz = is_zero(hn);
-        const double r_hn = rcp_nr(sel(hz, 1.0, hn));
+        const double r_hn = rcp_nr(sel1(hz, hn));
         RHP(i) = sel(hz, CST(inv_hmin), r_hn);                                           // next step's 1/hp (:51)
-        double ph = sel(hz, 0.0, -Ei_n * r_hn * CST(inv_Lf));                              // concentration :75-76
+        double ph = sel0(hz, -Ei_n * r_hn * CST(inv_Lf));                              // concentration :75-76
         if (ph > 1.0) ph = 1.0;                                                       // :77
-        Ei_n = sel(hz, 0.0, Ei_n);                                                          // :185
+        Ei_n = sel0(hz, Ei_n);                                                          // :185
         const double omn = 1 - ph;
         const double En = fma(ph, Ei_n, omn * Ew_n);                                  // :186
         const double Tn = fma(Ti[i], ph, omn * TW(i));                                // :187
