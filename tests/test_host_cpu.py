@@ -149,6 +149,25 @@ def test_solutions_assembly_layout():
     assert full.raw.E.shape == (300, 50) and np.isnan(full.raw.E).all() and abs(full.ts[-1] - 2.995) < 1e-12
 
 
+def test_checkpoint_roundtrip(tmp_path):
+    rng = np.random.default_rng(3)
+    final = {k: rng.normal(size=(5, 37)) for k in ("Ei", "Ew", "h", "D", "phi", "T0")}
+    final["Ew"][2, 3] = np.nan
+    path = str(tmp_path / "state.ebm")
+    ebm.save_state(path, final, years_done=12)
+    back, years = ebm.load_state(path)
+    assert years == 12 and list(back) == list(final)
+    for k in final:
+        assert np.array_equal(back[k], final[k], equal_nan=True)
+    inits, T0 = ebm.inits_from_state(back)
+    assert len(inits) == 5 and "T0" not in inits[0] and np.array_equal(inits[4].D, final["D"][4]) and T0.shape == (5, 37)
+    assert os.path.getsize(path) == 8 + 32 + 6 * (16 + 8 * 5 * 37)
+    with open(path, "r+b") as fh:
+        fh.write(b"XXXXXXXX")
+    with pytest.raises(ValueError):
+        ebm.load_state(path)
+
+
 def test_member_block_partition():
     for total in (0, 1, 7, 64, 65536, 1048576 + 3):
         for world in (1, 2, 3, 8):
