@@ -124,7 +124,8 @@ __global__ void classic_strict_kernel(const ClassicKArgs a, double* ws) {
     for (int ti = 1; ti <= nt; ++ti) {
       const long long tinx = (long long)year * nt + ti;
       const double f = ebm_forcing_eval(fr[0], fr[1 * nmem], fr[2 * nmem], fr[3 * nmem], fr[4 * nmem], fr[6 * nmem],
-                                        fr[7 * nmem], fr[8 * nmem], fr[9 * nmem], ebm_global_time(tinx, nt));
+                                        fr[7 * nmem], fr[8 * nmem], fr[9 * nmem],
+                                        ebm_global_time(tinx + (long long)a.start_year * nt, nt));
       classic_step_literal(a.g, p, nmem, s, ti, f, E, Tg, Tc, dg, y, w, nmem);
       for (int j = 0; j < nx; ++j) {
         const double Ej = E[j * nmem];

@@ -561,7 +561,7 @@ __global__ void __maxnreg__(MAXR) classic_uniform_kernel(const ClassicKArgs a) {
       S1c_next = S1c1;
       double f = fbase;
       if (!constf) {
-        const long long tinx = (long long)year * nt + ti;
+        const long long tinx = (long long)(year + a.start_year) * nt + ti;
         f = ebm_forcing_eval(fr[0 * MW + mi], fr[1 * MW + mi], fr[2 * MW + mi], fr[3 * MW + mi], fr[4 * MW + mi],
                              fr[6 * MW + mi], fr[7 * MW + mi], fr[8 * MW + mi], fr[9 * MW + mi],
                              ebm_global_time(tinx, nt));

@@ -213,6 +213,7 @@ extern "C" int32_t ebm_classic_run_device(const ebm_grid_t* grid, const ebm_clas
   a.nx = grid->nx; a.nt = grid->nt; a.dur = grid->dur; a.nmem = args->nmem;
   a.winter_inx = grid->winter_inx; a.summer_inx = grid->summer_inx;
   a.lastonly = opt.lastonly; a.field_stride = opt.field_stride;
+  a.start_year = opt.start_year > 0 ? opt.start_year : 0;
   a.par = args->par; a.forc = args->forc; a.E = args->E; a.Tg = args->Tg;
   a.diag = args->diag; a.seasonal = args->seasonal; a.raw = args->raw; a.flags = args->flags;
   const int ypl = opt.years_per_launch > 0 ? opt.years_per_launch : grid->dur;
@@ -329,6 +330,7 @@ extern "C" int32_t ebm_miz_run_device(const ebm_grid_t* grid, const ebm_miz_devi
   a.maxit = opt.newton_maxit > 0 ? opt.newton_maxit : 100;
   a.tol = opt.newton_tol > 0.0 ? opt.newton_tol : 1e-8;
   a.step_limit = opt.step_limit > 0 ? opt.step_limit : 0;
+  a.start_year = opt.start_year > 0 ? opt.start_year : 0;
   a.par = args->par; a.forc = args->forc;
   a.Ei = args->Ei; a.Ew = args->Ew; a.h = args->h; a.D = args->D; a.phi = args->phi; a.T0 = args->T0;
   a.diag = args->diag; a.seasonal = args->seasonal; a.raw = args->raw;

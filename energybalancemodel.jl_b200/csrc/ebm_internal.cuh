@@ -42,6 +42,7 @@ struct ClassicKArgs {
   int nx, nt, dur, W;
   long long nmem;
   int year0, nyears;             // integrate years [year0, year0+nyears), 0-based
+  int start_year;                // years already simulated before this run: added to the time passed to Forcing
   int winter_inx, summer_inx, lastonly, field_stride, all_const_forcing;
   int uniform_split;             // 1: classic_uniform.cu integrates parameter-uniform 32-member groups, classic_bands.cu the rest
   EbmGridTables g;
@@ -57,6 +58,7 @@ struct MizKArgs {
   int year0, nyears;
   int winter_inx, summer_inx, lastonly, field_stride, all_const_forcing;
   int maxit; double tol;
+  int start_year;                  // years already simulated before this run (Forcing time offset)
   int step_limit;                  // > 0: stop after this many steps of the run (partial last year)
   int single_ti; double single_f;  // > 0: exactly one step at year-index single_ti with forcing single_f (ebm_miz_step)
   EbmGridTables g;

@@ -320,7 +320,7 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) miz_fast_kernel(const MizKA
       if (!constf)
         f = ebm_forcing_eval(cst[cF0], cst[cF0 + 1], cst[cF0 + 2], cst[cF0 + 3], cst[cF0 + 4], cst[cF0 + 6], cst[cF0 + 7],
                              cst[cF0 + 8], cst[cF0 + 9],
-                             ebm_global_time((long long)year * nt + ti, nt));
+                             ebm_global_time((long long)(year + a.start_year) * nt + ti, nt));
       const double fA = f - CST(A);
       const int season = (ti == a.winter_inx) ? 0 : (ti == a.summer_inx) ? 1 : (ti == nt) ? 2 : -1;
 

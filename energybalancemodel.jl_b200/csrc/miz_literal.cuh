@@ -436,7 +436,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) miz_warp_kernel(const MizKA
       if (a.single_ti > 0) f = a.single_f;
       else if (!constf)
         f = ebm_forcing_eval(fr[0], fr[1], fr[2], fr[3], fr[4], fr[6], fr[7], fr[8], fr[9],
-                             ebm_global_time((long long)year * nt + ti, nt));
+                             ebm_global_time((long long)(year + a.start_year) * nt + ti, nt));
       const int season = (ti == a.winter_inx) ? 0 : (ti == a.summer_inx) ? 1 : (ti == nt) ? 2 : -1;
 
       // ---- temperatures (miz.jl:156-158)

@@ -80,7 +80,7 @@ def integrate_ensemble(model, st: SpaceTime, forcings, pars, inits, *, lastonly:
                        want_diag: bool = True, want_seasonal: bool | None = None, want_raw: bool | None = None,
                        device: int = -1, strict: bool = False, years_per_launch: int = 0, debug=None,
                        newton_tol: float = 0.0, newton_maxit: int = 0, T0guess=None,
-                       step_limit: int = 0) -> EnsembleResult:
+                       step_limit: int = 0, start_year: int = 0) -> EnsembleResult:
     """Integrate ``len(pars)`` independent members on one GPU.
 
     ``field_stride`` > 0 selects the members (``m % field_stride == 0``) whose seasonal (L1) and raw (L2)
@@ -96,7 +96,7 @@ def integrate_ensemble(model, st: SpaceTime, forcings, pars, inits, *, lastonly:
     nx, nt, dur = st.nx, st.nt, st.dur
     grid = _lib.make_grid(st)
     opt = _lib.make_options(device, lastonly, field_stride, strict, years_per_launch, newton_maxit, newton_tol,
-                            step_limit)
+                            step_limit, start_year)
     forc = np.ascontiguousarray(np.stack([f.row() for f in forcings]))
     nsel = (nmem + field_stride - 1) // field_stride if field_stride > 0 else 0
     nraw = nt if lastonly else nt * dur

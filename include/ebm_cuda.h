@@ -94,7 +94,8 @@ typedef struct ebm_options {
                                steps not taken stay NaN).  Used to compare short horizons from a given state: the
                                MIZ dynamics amplify rounding differences, so long-run pointwise
                                parity is not defined even for the reference itself. */
-  int32_t reserved;
+  int32_t start_year;       /* years already simulated before this run (restart): Forcing is evaluated at
+                               T + start_year; output slots stay indexed from the start of this run */
 } ebm_options_t;
 
 /* ---- outputs (host entry points).  Any pointer may be NULL = not wanted. ------------------------

@@ -38,7 +38,7 @@ struct CGrid
 end
 struct COptions
     device::Int32; lastonly::Int32; field_stride::Int32; strict::Int32; years_per_launch::Int32
-    newton_maxit::Int32; newton_tol::Float64; step_limit::Int32; reserved::Int32
+    newton_maxit::Int32; newton_tol::Float64; step_limit::Int32; start_year::Int32
 end
 struct CClassicOutputs
     diag::Ptr{Float64}; seasonal::Ptr{Float64}; raw::Ptr{Float64}; E_final::Ptr{Float64}; Tg_final::Ptr{Float64}

@@ -155,7 +155,7 @@ def test_restart_through_checkpoint_file_is_exact(tmp_path):
     """the classic model restarts exactly from the returned (E, Tg) -- the reference cannot, Tg is not a
     stored variable (infrastructure.jl:621).  4 years == 2 + 2 years through a checkpoint file, bit for bit."""
     par = _par()
-    forcings = [ebm.Forcing(-3.0), ebm.Forcing(2.0)]
+    forcings = [ebm.Forcing(-3.0), ebm.Forcing(0.0, 4.0, -2.0, (1, 0), (2.0, -6.0))]   # constant, and a ramp over years 1..3
     inits = [cold_init(100), warm_init(100)]
     full = ebm.integrate_ensemble("Classic", ebm.SpaceTime(100, 2000, 4), forcings, [par] * 2, inits)
     st2 = ebm.SpaceTime(100, 2000, 2)
@@ -164,7 +164,7 @@ def test_restart_through_checkpoint_file_is_exact(tmp_path):
     ebm.save_state(path, a.final, years_done=2)
     state, years = ebm.load_state(path)
     inits2, _ = ebm.inits_from_state(state)
-    b = ebm.integrate_ensemble("Classic", st2, forcings, [par] * 2, inits2)
+    b = ebm.integrate_ensemble("Classic", st2, forcings, [par] * 2, inits2, start_year=years)   # Forcing sees T + 2
     assert years == 2
     assert np.array_equal(full.final["E"], b.final["E"]) and np.array_equal(full.final["Tg"], b.final["Tg"])
     assert np.array_equal(full.diag[:, 2:], b.diag)

@@ -42,7 +42,7 @@ def test_struct_layouts_match_the_header():
 #include "ebm_cuda.h"
 int main(void) {
   printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(ebm_grid_t), offsetof(ebm_grid_t, x), sizeof(ebm_options_t),
-         offsetof(ebm_options_t, newton_tol), offsetof(ebm_options_t, step_limit), sizeof(ebm_classic_outputs_t),
+         offsetof(ebm_options_t, newton_tol), offsetof(ebm_options_t, start_year), sizeof(ebm_classic_outputs_t),
          sizeof(ebm_miz_outputs_t), sizeof(ebm_classic_device_args_t), sizeof(ebm_miz_device_args_t), sizeof(ebm_forcing_t));
   printf("%d %d %d\n", EBM_CLASSIC_NPAR, EBM_MIZ_NPAR, EBM_NFORCING);
   return 0;
@@ -56,7 +56,7 @@ int main(void) {
         os.remove(exe)
     got = list(map(int, out))
     want = [C.sizeof(_lib.Grid), _lib.Grid.x.offset, C.sizeof(_lib.Options), _lib.Options.newton_tol.offset,
-            _lib.Options.step_limit.offset, C.sizeof(_lib.ClassicOutputs), C.sizeof(_lib.MizOutputs),
+            _lib.Options.start_year.offset, C.sizeof(_lib.ClassicOutputs), C.sizeof(_lib.MizOutputs),
             C.sizeof(_lib.ClassicDeviceArgs), C.sizeof(_lib.MizDeviceArgs), 8 * _lib.NFORCING,
             _lib.CLASSIC_NPAR, _lib.MIZ_NPAR, _lib.NFORCING]
     assert got == want, (got, want)
