@@ -116,19 +116,21 @@ __device__ __forceinline__ void diffuse(const double* __restrict__ lo, const dou
 }
 
 // ---- tridiagonal solve across the warp, K rows per lane; rhs -> solution -----------------------------------------------
-template <int K>
-__device__ __forceinline__ void tridiag(int lane, const double (&jl)[K], const double (&jd)[K], const double (&ju)[K],
-                                        double (&rhs)[K]) {
+// row(i, jl, jd, ju) produces row i on demand, so the three coefficient vectors never live in registers at once
+template <int K, class RowFn>
+__device__ __forceinline__ void tridiag(int lane, RowFn row, double (&rhs)[K]) {
   // local forward elimination:  x_i + q_i x_{i+1} + s_i xL = y_i   (xL = last unknown of the previous lane)
   double q[K], s[K];
   {
     double qp = 0.0, yp = 0.0, sp = 0.0;
 #pragma unroll
     for (int i = 0; i < K; ++i) {
-      const double w = (i == 0) ? jd[i] : fma(-jl[i], qp, jd[i]);
+      double jl_i, jd_i, ju_i;
+      row(i, jl_i, jd_i, ju_i);
+      const double w = (i == 0) ? jd_i : fma(-jl_i, qp, jd_i);
       const double iw = rcp_nr(w);
-      const double tq = jl[i] * iw;
-      q[i] = ju[i] * iw;
+      const double tq = jl_i * iw;
+      q[i] = ju_i * iw;
       const double yi = (i == 0) ? rhs[i] * iw : fma(-tq, yp, rhs[i] * iw);
       const double si = (i == 0) ? tq : -tq * sp;
       s[i] = si; rhs[i] = yi;
@@ -364,20 +366,20 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) miz_fast_kernel(const MizKA
         if (__all_sync(kFull, ok)) break;
         if (__any_sync(kFull, nan) || it >= maxit) { fail = 1; break; }
         // generalised Jacobian  J = -diag(k/hp + B) + L*diag(phi*[T0 < Tm])
-        double g[K], jl[K], jd[K], ju[K];
-#pragma unroll
-        for (int i = 0; i < K; ++i) g[i] = (T0[i] < CST(Tm)) ? phi[i] : 0.0;
-        const double gleft = shfl_up1(g[K - 1]), gright = shfl_dn1(g[0]);
+        double g[K];
 #pragma unroll
         for (int i = 0; i < K; ++i) {
-          const int s = i * 32 + lane;
-          const double l = lo[s], u = up[s];
-          jd[i] = fma(-(l + u), g[i], -kb[i]);
-          jl[i] = l * ((i == 0) ? gleft : g[i - 1]);
-          ju[i] = u * ((i == K - 1) ? gright : g[i + 1]);
+          g[i] = (T0[i] < CST(Tm)) ? phi[i] : 0.0;
           res[i] = (lane * K + i >= nx) ? 0.0 : res[i];
         }
-        tridiag<K>(lane, jl, jd, ju, res);
+        const double gleft = shfl_up1(g[K - 1]), gright = shfl_dn1(g[0]);
+        tridiag<K>(lane, [&](int i, double& jl, double& jd, double& ju) {
+          const int s = i * 32 + lane;
+          const double l = lo[s], u = up[s];
+          jd = fma(-(l + u), g[i], -kb[i]);
+          jl = l * ((i == 0) ? gleft : g[i - 1]);
+          ju = u * ((i == K - 1) ? gright : g[i + 1]);
+        }, res);
         // The residual is piecewise linear: if the step leaves the active set [T0 < Tm] (where phi != 0) unchanged,
         // the new T0 is the root to rounding (|res| ~ 1e-12 << tol) and the confirming residual evaluation the
         // reference performs is skipped; the iteration count is the same either way.
