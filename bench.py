@@ -45,21 +45,33 @@ def parse():
     ap.add_argument("--members", type=int, default=0, help="members per GPU (default: 65536 classic, 131072 miz)")
     ap.add_argument("--years", type=int, default=0, help="simulated years (default: 200 classic, 50 miz)")
     ap.add_argument("--cpu-sample-members", type=int, default=0)
+    ap.add_argument("--order", default="interleaved", choices=["branch", "interleaved"],
+                    help="classic member order: SURVEY 8d's C4 definition (even members warm start, odd members cold start; "
+                         "default) or branch-major (all warm starts, then all cold starts)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()
 
 
 # ----------------------------------------------------------------------------- workloads
+ORDER = "interleaved"
+
+
 def classic_workload(ebm, nmem_total, offset, count, years):
-    """C4: F_m = -20 + 40*(m mod H)/(H-1); first half warm start, second half cold start (H = nmem_total/2)."""
+    """C4: H = nmem_total/2 forcings F = -20..+20, each run from a warm and from a cold start.  Member order
+    "interleaved" (SURVEY 8d, default): F_m = -20 + 40*(m//2)/(H-1), even m warm start, odd m cold start; "branch":
+    F_m = -20 + 40*(m mod H)/(H-1), first half warm, second half cold.  The library sorts members by regime itself."""
     st = ebm.SpaceTime(100, 2000, years)
     p = ebm.default_parameters("Classic")
     prow = np.array([p[k] for k in ebm.CLASSIC_PAR_ORDER])
     H = max(nmem_total // 2, 1)
     m = np.arange(offset, offset + count)
-    F = -20.0 + 40.0 * (m % H) / max(H - 1, 1)
-    warm = m < H
+    if ORDER == "interleaved":
+        F = -20.0 + 40.0 * (m // 2) / max(H - 1, 1)
+        warm = (m % 2) == 0
+    else:
+        F = -20.0 + 40.0 * (m % H) / max(H - 1, 1)
+        warm = m < H
     par = np.repeat(prow[None, :], count, axis=0)
     forc = np.zeros((count, 10))
     forc[:, 0] = forc[:, 1] = forc[:, 2] = F
@@ -186,7 +198,7 @@ def reference_arm(args, nmem, years):
 
 def workload_config(workload, nmem, years, gpus):
     if workload == "classic":
-        return {"workload": "C4 classic-EBM hysteresis ensemble: F=-20..+20 W/m^2, warm+cold start branches",
+        return {"workload": "C4 classic-EBM hysteresis ensemble: F=-20..+20 W/m^2, warm+cold start branches", "member_order": ORDER,
                 "members_per_gpu": nmem, "members_total": nmem * gpus, "years": years, "nx": 100, "nt": 2000,
                 "outputs": "L0 diagnostics (3 seasons x 4 scalars per member-year) + final state",
                 "l2": "flushed between timed iterations (256 MiB write); state is register-resident in any case"}
@@ -199,6 +211,8 @@ def workload_config(workload, nmem, years, gpus):
 # ----------------------------------------------------------------------------- GPU arm
 def main():
     args = parse()
+    global ORDER
+    ORDER = args.order
     nmem = args.members or (65536 if args.workload == "classic" else 131072)
     years = args.years or (200 if args.workload == "classic" else 50)
     if args.impl == "reference":
@@ -228,11 +242,23 @@ def main():
     grid = _lib.make_grid(st)
     opt = _lib.make_options(device=local, lastonly=True, field_stride=0)
 
-    # ---- device-resident inputs (member index fastest), allocated by torch
+    # ---- device-resident inputs (member index fastest), allocated by torch.  For the classic kernels (lane = member)
+    # the resident layout is sorted by the regime of the initial state, exactly what ebm_classic_run does internally
+    # for host buffers; member_index tells the library where each slot's output rows go (original member order).
     f64 = torch.float64
-    d_par = torch.from_numpy(np.ascontiguousarray(par.T)).to(dev)
-    d_forc = torch.from_numpy(np.ascontiguousarray(forc.T)).to(dev)
-    d_init = [torch.from_numpy(np.ascontiguousarray(a.T)).to(dev) for a in init]
+    slot_of = None
+    if args.workload == "classic":
+        ice = (init[0] < 0).sum(axis=1)
+        key = np.where(ice == 0, 0, np.where(ice == nx, 2, 1))
+        perm = np.argsort(key, kind="stable")
+        if not np.array_equal(perm, np.arange(nmem)):
+            slot_of = torch.from_numpy(perm.astype(np.int64)).to(dev)
+            par_d, forc_d, init_d = par[perm], forc[perm], [a[perm] for a in init]
+    if slot_of is None:
+        par_d, forc_d, init_d = par, forc, init
+    d_par = torch.from_numpy(np.ascontiguousarray(par_d.T)).to(dev)
+    d_forc = torch.from_numpy(np.ascontiguousarray(forc_d.T)).to(dev)
+    d_init = [torch.from_numpy(np.ascontiguousarray(a.T)).to(dev) for a in init_d]
     nstate = len(init) + (1 if args.workload == "miz" else 0)
     d_state = [torch.empty((nx, nmem), dtype=f64, device=dev) for _ in range(nstate)]
     d_diag = torch.full((nmem, years, 3, 4), float("nan"), dtype=f64, device=dev)
@@ -243,7 +269,8 @@ def main():
 
     if args.workload == "classic":
         dargs = _lib.ClassicDeviceArgs(nmem, d_par.data_ptr(), d_forc.data_ptr(), d_state[0].data_ptr(),
-                                       d_state[1].data_ptr(), d_diag.data_ptr(), None, None, d_flags.data_ptr())
+                                       d_state[1].data_ptr(), d_diag.data_ptr(), None, None, d_flags.data_ptr(),
+                                       slot_of.data_ptr() if slot_of is not None else None)
         run_dev = lambda: _lib.check(lib.ebm_classic_run_device(C.byref(grid), C.byref(dargs), C.byref(opt),
                                                                 C.c_void_p(stream.cuda_stream)))
     else:

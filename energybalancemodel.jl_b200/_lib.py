@@ -51,7 +51,8 @@ class MizOutputs(C.Structure):
 
 class ClassicDeviceArgs(C.Structure):
     _fields_ = [("nmem", C.c_int64), ("par", C.c_void_p), ("forc", C.c_void_p), ("E", C.c_void_p), ("Tg", C.c_void_p),
-                ("diag", C.c_void_p), ("seasonal", C.c_void_p), ("raw", C.c_void_p), ("flags", C.c_void_p)]
+                ("diag", C.c_void_p), ("seasonal", C.c_void_p), ("raw", C.c_void_p), ("flags", C.c_void_p),
+                ("member_index", C.c_void_p)]
 
 
 class MizDeviceArgs(C.Structure):

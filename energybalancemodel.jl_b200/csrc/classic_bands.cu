@@ -126,8 +126,9 @@ __global__ void __launch_bounds__(MAXT, MINB) classic_bands_kernel(const Classic
   }
   __syncthreads();
 
-  const bool sel = active && a.field_stride > 0 && (m % a.field_stride) == 0;
-  const long long msel = sel ? m / a.field_stride : 0;
+  const long long mo = a.orig != nullptr ? a.orig[m] : m;   // original member index: output rows
+  const bool sel = active && a.field_stride > 0 && (mo % a.field_stride) == 0;
+  const long long msel = sel ? mo / a.field_stride : 0;
   const long long nraw = a.lastonly ? (long long)nt : (long long)nt * a.dur;
   // Forcing{true}: base == peak == cool, all breakpoints 0 -> the call is the constant `base`
   const double fbase = fr[0 * MW + mi];
@@ -290,7 +291,7 @@ __global__ void __launch_bounds__(MAXT, MINB) classic_bands_kernel(const Classic
             const double* r4 = red + (b * 4) * MW + mi;
             t0 += r4[0 * MW]; t1 += r4[1 * MW]; t2 += r4[2 * MW]; t3 = fmin(t3, r4[3 * MW]);
           }
-          double* o = a.diag + ((m * a.dur + year) * 3 + season) * 4;
+          double* o = a.diag + ((mo * a.dur + year) * 3 + season) * 4;
           o[0] = t0; o[1] = t1; o[2] = kTwoPi * t2; o[3] = (t3 > 1.5) ? 1.0 : t3;
         }
       }
@@ -320,7 +321,7 @@ __global__ void __launch_bounds__(MAXT, MINB) classic_bands_kernel(const Classic
       bad = bad || !(fabs(E[i]) < 1e300) || !(fabs(Tg[i]) < 1e300);
     }
   }
-  if (bad && a.flags != nullptr) atomicOr(a.flags + m, 1);
+  if (bad && a.flags != nullptr) atomicOr(a.flags + mo, 1);
 }
 
 template <int K, int MW, int MAXT, int MINB>

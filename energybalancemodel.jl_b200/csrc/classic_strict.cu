@@ -115,8 +115,9 @@ __global__ void classic_strict_kernel(const ClassicKArgs a, double* ws) {
   const ClassicStatics s = make_statics(p, nmem, nt);
   const double Lf = p[12 * nmem];
   const double* fr = a.forc + m;
-  const bool sel = a.field_stride > 0 && (m % a.field_stride) == 0;
-  const long long msel = sel ? m / a.field_stride : 0;
+  const long long mo = a.orig != nullptr ? a.orig[m] : m;   // original member index: output rows
+  const bool sel = a.field_stride > 0 && (mo % a.field_stride) == 0;
+  const long long msel = sel ? mo / a.field_stride : 0;
   const long long nraw = a.lastonly ? (long long)nt : (long long)nt * a.dur;
   for (int j = 0; j < nx; ++j) { sE[j * nmem] = 0.0; sT[j * nmem] = 0.0; sH[j * nmem] = 0.0; }
 
@@ -158,7 +159,7 @@ __global__ void classic_strict_kernel(const ClassicKArgs a, double* ws) {
         if (a.diag != nullptr) {
           double edge = 1.0; bool found = false;
           for (int j = 0; j < nx && !found; ++j) if (vE(j) < 0.0) { edge = a.g.x[j]; found = true; }
-          double* o = a.diag + ((m * a.dur + year) * 3 + season) * 4;
+          double* o = a.diag + ((mo * a.dur + year) * 3 + season) * 4;
           o[0] = hemi_mean(a.g.x, nx, vT);
           o[1] = hemi_mean(a.g.x, nx, vE);
           o[2] = Lit::mul(Lit::mul(2.0, kPi), hemi_mean(a.g.x, nx, [&](int j) { return vE(j) < 0.0 ? 1.0 : 0.0; }));
@@ -171,7 +172,7 @@ __global__ void classic_strict_kernel(const ClassicKArgs a, double* ws) {
   if (a.flags != nullptr) {
     bool bad = false;
     for (int j = 0; j < nx; ++j) bad = bad || !(fabs(E[j * nmem]) < 1e300) || !(fabs(Tg[j * nmem]) < 1e300);
-    if (bad) atomicOr(a.flags + m, 1);
+    if (bad) atomicOr(a.flags + mo, 1);
   }
 }
 

@@ -94,7 +94,7 @@ struct Ctx {
   // 16 members of 2 bands; thread-private [i][thread] (conflict free) when a warp holds all bands of 4 members
   __device__ __forceinline__ int cidx(int i) const { return WARPM ? (i * (WB * MW) + (int)threadIdx.x) : ((j0 + i) * MW + mi); }
   bool active, sel, cta_fields;
-  long long m, msel;
+  long long m, mo, msel;   // slot in this launch, original member index (output rows), index among field-output members
   // state
   double E[K], Tg[K], accT;
   RowStore<K, QS_SMEM> rs;
@@ -331,7 +331,7 @@ struct Ctx {
           dgA += __shfl_xor_sync(kFull, dgA, o); dgX = fmin(dgX, __shfl_xor_sync(kFull, dgX, o));
         }
         if (band == 0 && a.diag != nullptr && active) {
-          double* o = a.diag + ((m * a.dur + year) * 3 + season) * 4;
+          double* o = a.diag + ((mo * a.dur + year) * 3 + season) * 4;
           o[0] = dgT; o[1] = dgE; o[2] = kTwoPi * dgA; o[3] = (dgX > 1.5) ? 1.0 : dgX;
         }
       }
@@ -396,7 +396,7 @@ struct Ctx {
           t1 += r4[1 * MW]; t2 += r4[2 * MW]; t3 = fmin(t3, r4[3 * MW]);
           t0 += r4[0 * MW];
         }
-        double* o = a.diag + ((m * a.dur + year) * 3 + season) * 4;
+        double* o = a.diag + ((mo * a.dur + year) * 3 + season) * 4;
         o[0] = t0; o[1] = t1; o[2] = kTwoPi * t2; o[3] = (t3 > 1.5) ? 1.0 : t3;
       }
     }
@@ -530,8 +530,10 @@ __global__ void __maxnreg__(MAXR) classic_uniform_kernel(const ClassicKArgs a) {
   cx.inv_nt = 1.0 / nt; cx.inv_Lf = 1.0 / pLf;
   cx.band = band; cx.mi = mi; cx.j0 = band * K;
   cx.active = active;
-  cx.sel = active && a.field_stride > 0 && (m % a.field_stride) == 0;
-  cx.msel = cx.sel ? m / a.field_stride : 0;
+  const long long mo = a.orig != nullptr ? a.orig[m] : m;   // ebm_classic_device_args_t.member_index
+  cx.mo = mo;
+  cx.sel = active && a.field_stride > 0 && (mo % a.field_stride) == 0;
+  cx.msel = cx.sel ? mo / a.field_stride : 0;
   cx.m = m;
   cx.cta_fields = __syncthreads_or(cx.sel && (a.seasonal != nullptr)) != 0;
   cx.accT = 0.0;
@@ -582,7 +584,7 @@ __global__ void __maxnreg__(MAXR) classic_uniform_kernel(const ClassicKArgs a) {
       bad = bad || !(fabs(cx.E[i]) < 1e300) || !(fabs(cx.Tg[i]) < 1e300);
     }
   }
-  if (bad && a.flags != nullptr) atomicOr(a.flags + m, 1);
+  if (bad && a.flags != nullptr) atomicOr(a.flags + mo, 1);
 }
 
 template <int K, int WB, int MW, int MAXR, bool QS_SMEM = false, bool WARPM = false>

@@ -216,6 +216,7 @@ extern "C" int32_t ebm_classic_run_device(const ebm_grid_t* grid, const ebm_clas
   a.start_year = opt.start_year > 0 ? opt.start_year : 0;
   a.par = args->par; a.forc = args->forc; a.E = args->E; a.Tg = args->Tg;
   a.diag = args->diag; a.seasonal = args->seasonal; a.raw = args->raw; a.flags = args->flags;
+  a.orig = (const long long*)args->member_index;
   const int ypl = opt.years_per_launch > 0 ? opt.years_per_launch : grid->dur;
   for (int y0 = 0; y0 < grid->dur; y0 += ypl) {
     a.year0 = y0;
@@ -256,10 +257,45 @@ extern "C" int32_t ebm_classic_run(const ebm_grid_t* grid, int64_t nmem, const e
   EBM_TRY(B.alloc(&dforc, (size_t)nmem * EBM_NFORCING));
   EBM_TRY(B.alloc(&dE, (size_t)nmem * nx));
   EBM_TRY(B.alloc(&dTg, (size_t)nmem * nx));
-  EBM_TRY(upload_transposed((const double*)par, stage, dpar, nmem, EBM_CLASSIC_NPAR, s));
-  EBM_TRY(upload_transposed((const double*)forc, stage, dforc, nmem, EBM_NFORCING, s));
-  EBM_TRY(upload_transposed(E0, stage, dE, nmem, nx, s));
-  EBM_TRY(upload_transposed(Tg0, stage, dTg, nmem, nx, s));
+  // Lanes of a warp are members: members in different regimes (snowball next to ice free) make every warp take
+  // both code paths.  Sort the members by the regime of their initial state (stable: the caller's order survives
+  // within a regime); the kernels write every output row at the member's original index (member_index).
+  std::vector<long long> perm;
+  long long* dperm = nullptr;
+  if (!opt.strict && nmem > 32 && !getenv("EBM_NO_REORDER")) {
+    std::vector<unsigned char> key((size_t)nmem);
+    bool sorted = true;
+    for (long long m = 0; m < nmem; ++m) {
+      int ice = 0;
+      for (int j = 0; j < nx; ++j) ice += E0[m * nx + j] < 0.0;
+      key[m] = ice == 0 ? 0 : (ice == nx ? 2 : 1);        // 0 ice free, 1 partial cover, 2 every cell ice
+      if (m > 0 && key[m] < key[m - 1]) sorted = false;
+    }
+    if (!sorted) {
+      perm.resize((size_t)nmem);
+      long long pos = 0;
+      for (int k = 0; k < 3; ++k)
+        for (long long m = 0; m < nmem; ++m)
+          if (key[m] == k) perm[pos++] = m;               // perm[slot] = original index
+      EBM_TRY(B.alloc(&dperm, (size_t)nmem));
+      EBM_CUDA_TRY(cudaMemcpyAsync(dperm, perm.data(), sizeof(long long) * nmem, cudaMemcpyHostToDevice, s));
+    }
+  }
+  auto upload = [&](const double* host, double* dst, long long cols) -> int {
+    if (!dperm) return upload_transposed(host, stage, dst, nmem, cols, s);
+    EBM_CUDA_TRY(cudaMemcpyAsync(stage, host, sizeof(double) * nmem * cols, cudaMemcpyHostToDevice, s));
+    return ebm_launch_gather_transpose(stage, dst, nmem, cols, dperm, 0, s);
+  };
+  auto download = [&](double* host, const double* src) -> int {      // device [nx][slots] -> host [nmem][nx], original order
+    if (!dperm) return download_transposed(host, stage, src, nx, nmem, s);
+    EBM_TRY(ebm_launch_gather_transpose(src, stage, nmem, nx, dperm, 1, s));
+    EBM_CUDA_TRY(cudaMemcpyAsync(host, stage, sizeof(double) * nmem * nx, cudaMemcpyDeviceToHost, s));
+    return EBM_OK;
+  };
+  EBM_TRY(upload((const double*)par, dpar, EBM_CLASSIC_NPAR));
+  EBM_TRY(upload((const double*)forc, dforc, EBM_NFORCING));
+  EBM_TRY(upload(E0, dE, nx));
+  EBM_TRY(upload(Tg0, dTg, nx));
   const double kNaN = NAN;
   const size_t ndiag = (size_t)nmem * dur * EBM_NSEASON * EBM_NDIAG;
   const size_t nseas = (size_t)nsel * dur * EBM_NSEASON * EBM_CLASSIC_NVAR * nx;
@@ -272,13 +308,14 @@ extern "C" int32_t ebm_classic_run(const ebm_grid_t* grid, int64_t nmem, const e
   memset(&da, 0, sizeof(da));
   da.nmem = nmem; da.par = dpar; da.forc = dforc; da.E = dE; da.Tg = dTg;
   da.diag = ddiag; da.seasonal = dseas; da.raw = draw; da.flags = dflags;
+  da.member_index = (const int64_t*)dperm;
   EBM_TRY(ebm_classic_run_device(grid, &da, &opt, s));
   if (out->diag) EBM_CUDA_TRY(cudaMemcpyAsync(out->diag, ddiag, sizeof(double) * ndiag, cudaMemcpyDeviceToHost, s));
   if (out->seasonal) EBM_CUDA_TRY(cudaMemcpyAsync(out->seasonal, dseas, sizeof(double) * nseas, cudaMemcpyDeviceToHost, s));
   if (out->raw) EBM_CUDA_TRY(cudaMemcpyAsync(out->raw, draw, sizeof(double) * nrawn, cudaMemcpyDeviceToHost, s));
   if (out->flags) EBM_CUDA_TRY(cudaMemcpyAsync(out->flags, dflags, sizeof(int) * nmem, cudaMemcpyDeviceToHost, s));
-  if (out->E_final) { EBM_TRY(download_transposed(out->E_final, stage, dE, nx, nmem, s)); EBM_CUDA_TRY(cudaStreamSynchronize(s)); }
-  if (out->Tg_final) { EBM_TRY(download_transposed(out->Tg_final, stage, dTg, nx, nmem, s)); }
+  if (out->E_final) { EBM_TRY(download(out->E_final, dE)); EBM_CUDA_TRY(cudaStreamSynchronize(s)); }
+  if (out->Tg_final) { EBM_TRY(download(out->Tg_final, dTg)); }
   EBM_CUDA_TRY(cudaStreamSynchronize(s));
   return EBM_OK;
 }

@@ -50,6 +50,7 @@ struct ClassicKArgs {
   const double* forc;            // [10][nmem]
   double* E; double* Tg;         // [nx][nmem]
   double* diag; double* seasonal; double* raw; int* flags;
+  const long long* orig;         // NULL or [nmem]: original member index of slot m (output rows, field selection)
 };
 
 struct MizKArgs {
@@ -84,6 +85,9 @@ int ebm_launch_miz_single_step(const EbmGridTables& g, const double* par22, int 
                                double* vars_out, long long* iters, cudaStream_t stream);
 int ebm_launch_transpose(const double* src, double* dst, long long rows, long long cols, cudaStream_t stream);
 int ebm_launch_fill(double* dst, long long n, double v, cudaStream_t stream);
+// dst[c][r] = src[idx[r]][c] (rows x cols -> cols x rows with a row gather); inverse: dst[idx[r]][c] = src[c][r]
+int ebm_launch_gather_transpose(const double* src, double* dst, long long rows, long long cols, const long long* idx,
+                                int inverse, cudaStream_t stream);
 int ebm_run_fp64_peak(int device, double* tflops, double* mhz);
 
 // ----------------------------------------------------------------------------- small device helpers

@@ -18,6 +18,17 @@ __global__ void transpose_kernel(const double* __restrict__ src, double* __restr
   }
 }
 
+// member reordering: forward  dst[c*rows + r] = src[idx[r]*cols + c];  inverse  dst[idx[r]*cols + c] = src[c*rows + r]
+__global__ void gather_transpose_kernel(const double* __restrict__ src, double* __restrict__ dst, long long rows, long long cols,
+                                        const long long* __restrict__ idx, int inverse) {
+  const long long n = rows * cols;
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (long long)gridDim.x * blockDim.x) {
+    const long long c = q / rows, r = q % rows;     // consecutive threads: consecutive members of one column
+    if (inverse) dst[idx[r] * cols + c] = src[q];
+    else dst[q] = src[idx[r] * cols + c];
+  }
+}
+
 __global__ void fill_kernel(double* dst, long long n, double v) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     dst[i] = v;
@@ -47,6 +58,15 @@ int ebm_launch_transpose(const double* src, double* dst, long long rows, long lo
   dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32));
   if (grid.y > 65535) { ebm_set_error("transpose: too many rows (%lld)", rows); return EBM_ERR_INVALID; }
   transpose_kernel<<<grid, block, 0, stream>>>(src, dst, rows, cols);
+  EBM_CUDA_TRY(cudaGetLastError());
+  ebm_count_launch();
+  return EBM_OK;
+}
+
+int ebm_launch_gather_transpose(const double* src, double* dst, long long rows, long long cols, const long long* idx,
+                                int inverse, cudaStream_t stream) {
+  if (rows <= 0 || cols <= 0) return EBM_OK;
+  gather_transpose_kernel<<<1184, 256, 0, stream>>>(src, dst, rows, cols, idx, inverse);
   EBM_CUDA_TRY(cudaGetLastError());
   ebm_count_launch();
   return EBM_OK;

@@ -132,6 +132,10 @@ typedef struct ebm_classic_device_args {
   double* seasonal;   /* NULL or [nsel][dur][3][3][nx] */
   double* raw;        /* NULL or [nsel][nraw][3][nx] */
   int32_t* flags;     /* NULL or [nmem], zero-initialised by the caller */
+  const int64_t* member_index; /* NULL, or [nmem] (device): original index of the member held in slot m.  Output rows
+                         (diag, flags) and the field_stride selection use it, so a caller may hand the members over in
+                         any order -- e.g. sorted by regime, which is what ebm_classic_run does internally: lanes of a
+                         warp are members, and neighbouring members in the same regime do not diverge */
 } ebm_classic_device_args_t;
 
 typedef struct ebm_miz_device_args {
