@@ -401,8 +401,9 @@ def run_e2e(args, ebm, lib, _lib, st, par, forc, init, nmem, years, local, world
                                                   C.byref(opt), C.byref(out)))
     h2d = sum(t.numel() * 8 for t in [h_par, h_forc] + h_init)
     d2h = h_diag.numel() * 8 + sum(t.numel() * 8 for t in h_fin)
-    # the library, context and grid tables are warm from the device-resident steps above; the host path's own
-    # allocations (cudaMalloc / cudaFree per call) are part of what a user pays and stay inside the timed region
+    # one untimed call first: the library keeps its device workspace between calls (a user integrating in a loop pays
+    # the cudaMalloc of the GB-sized staging buffers once), everything else -- H2D, reorder, kernel, D2H -- is timed
+    call()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()

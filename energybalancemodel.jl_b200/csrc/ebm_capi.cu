@@ -141,15 +141,48 @@ int select_device(const ebm_options_t& o) {
   return EBM_OK;
 }
 
-// RAII for the host-entry scratch allocations
+// Device workspace of the host entry points.  cudaMalloc / cudaFree of the GB-sized staging and output buffers cost
+// up to hundreds of milliseconds per call, so freed blocks are kept per device and reused by the next call
+// (released by ebm_shutdown, or when an allocation fails).
+struct WsBlock { int device; void* ptr; size_t bytes; bool in_use; };
+std::mutex g_ws_mu;
+std::vector<WsBlock> g_ws;
+
+void ws_release_free_blocks(int device) {   // caller holds g_ws_mu
+  for (size_t i = 0; i < g_ws.size();) {
+    if (!g_ws[i].in_use && (device < 0 || g_ws[i].device == device)) {
+      cudaFree(g_ws[i].ptr);
+      g_ws[i] = g_ws.back(); g_ws.pop_back();
+    } else ++i;
+  }
+}
+
 struct DevBufs {
   std::vector<void*> ptrs;
-  ~DevBufs() { for (void* p : ptrs) cudaFree(p); }
+  ~DevBufs() {
+    std::lock_guard<std::mutex> lk(g_ws_mu);
+    for (void* p : ptrs)
+      for (auto& b : g_ws) if (b.ptr == p) b.in_use = false;
+  }
   template <typename T>
   int alloc(T** out, size_t count) {
+    const size_t bytes = sizeof(T) * (count ? count : 1);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lk(g_ws_mu);
+    WsBlock* best = nullptr;
+    for (auto& b : g_ws)
+      if (!b.in_use && b.device == dev && b.bytes >= bytes && b.bytes <= 2 * bytes + 4096 && (!best || b.bytes < best->bytes)) best = &b;
+    if (best) { best->in_use = true; ptrs.push_back(best->ptr); *out = (T*)best->ptr; return EBM_OK; }
     void* p = nullptr;
-    cudaError_t e = cudaMalloc(&p, sizeof(T) * (count ? count : 1));
-    if (e != cudaSuccess) { cudaGetLastError(); ebm_set_error("cudaMalloc of %zu bytes failed: %s", sizeof(T) * count, cudaGetErrorString(e)); return EBM_ERR_OOM; }
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) {   // give cached blocks back and retry once
+      cudaGetLastError();
+      ws_release_free_blocks(dev);
+      e = cudaMalloc(&p, bytes);
+    }
+    if (e != cudaSuccess) { cudaGetLastError(); ebm_set_error("cudaMalloc of %zu bytes failed: %s", bytes, cudaGetErrorString(e)); return EBM_ERR_OOM; }
+    g_ws.push_back(WsBlock{dev, p, bytes, true});
     ptrs.push_back(p);
     *out = (T*)p;
     return EBM_OK;
@@ -179,6 +212,10 @@ extern "C" int32_t ebm_shutdown(void) {
   cudaGetDevice(&cur);
   for (auto& e : g_cache) { cudaSetDevice(e.device); cudaFree(e.dev); }
   g_cache.clear();
+  {
+    std::lock_guard<std::mutex> lk2(g_ws_mu);
+    ws_release_free_blocks(-1);
+  }
   cudaSetDevice(cur);
   cudaGetLastError();
   return EBM_OK;
