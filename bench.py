@@ -334,6 +334,9 @@ def main():
     diag_bytes = d_diag.numel() * 8
     roof = {"bound": "fp64", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
             "traffic": None,
+            "traffic_note": "not captured for this launch; ncu --set full on the short profiling command (profiles/README.md): "
+                            "classic 29.7 MB read + 0.7 MB written, MIZ 73 MB + 26 MB per launch -- initial state in, "
+                            "diagnostics and final state out; the kernels are FP64-bound, not HBM-bound",
             "peak_source": "measured in this run by ebm_fp64_peak (dependent-free DFMA chains); "
                            "MEASURED_PEAKS.json has no FP64 entry",
             "peak_nominal": NOMINAL_FP64_TFLOPS, "frac_of_nominal": achieved / NOMINAL_FP64_TFLOPS,
