@@ -16,7 +16,7 @@ from . import _lib
 from .types import (CLASSIC_PAR_ORDER, CLASSIC_VARS, MIZ_PAR_ORDER, MIZ_VARS, Collection, Forcing, Solutions,
                     SpaceTime)
 
-__all__ = ["integrate", "integrate_ensemble", "step", "EnsembleResult", "fp64_peak", "model_name"]
+__all__ = ["integrate", "integrate_ensemble", "integrate_arrays", "step", "EnsembleResult", "fp64_peak", "model_name"]
 
 _MIZ_STATE = ("Ei", "Ew", "h", "D", "phi")
 _CLASSIC_STATE = ("E", "Tg")
@@ -76,15 +76,13 @@ def _stack(inits, key, nx) -> np.ndarray:
     return a
 
 
-def integrate_ensemble(model, st: SpaceTime, forcings, pars, inits, *, lastonly: bool = True, field_stride: int = 0,
-                       want_diag: bool = True, want_seasonal: bool | None = None, want_raw: bool | None = None,
-                       device: int = -1, strict: bool = False, years_per_launch: int = 0, debug=None,
-                       newton_tol: float = 0.0, newton_maxit: int = 0, T0guess=None,
-                       step_limit: int = 0, start_year: int = 0) -> EnsembleResult:
-    """Integrate ``len(pars)`` independent members on one GPU.
+def integrate_ensemble(model, st: SpaceTime, forcings, pars, inits, *, T0guess=None, debug=None, **kw) -> EnsembleResult:
+    """Integrate ``len(pars)`` independent members on one GPU: one ``Forcing`` / parameter ``Collection`` / initial
+    condition ``Collection`` per member (the ensemble form of the reference's ``integrate`` arguments).
 
     ``field_stride`` > 0 selects the members (``m % field_stride == 0``) whose seasonal (L1) and raw (L2)
-    fields are returned; L0 diagnostics and final states are returned for every member.
+    fields are returned; L0 diagnostics and final states are returned for every member.  Keyword arguments as
+    ``integrate_arrays``.
     """
     name = model_name(model)
     if debug is not None:
@@ -92,12 +90,50 @@ def integrate_ensemble(model, st: SpaceTime, forcings, pars, inits, *, lastonly:
     nmem = len(pars)
     if not (len(forcings) == nmem == len(inits)) or nmem == 0:
         raise ValueError("forcings, pars and inits must be non-empty and of equal length")
+    forc = np.stack([f.row() for f in forcings])
+    if name == "Classic":
+        par = _rows(pars, CLASSIC_PAR_ORDER)
+        state = {k: _stack(inits, k, st.nx) for k in _CLASSIC_STATE}
+    else:
+        par = _rows(pars, MIZ_PAR_ORDER)
+        state = {k: _stack(inits, k, st.nx) for k in _MIZ_STATE}
+        if T0guess is not None:
+            state["T0"] = np.asarray(T0guess, dtype=np.float64).reshape(nmem, st.nx)
+    return integrate_arrays(name, st, forc, par, state, **kw)
+
+
+def integrate_arrays(model, st: SpaceTime, forc, par, state, *, lastonly: bool = True, field_stride: int = 0,
+                     want_diag: bool = True, want_seasonal: bool | None = None, want_raw: bool | None = None,
+                     device: int = -1, strict: bool = False, years_per_launch: int = 0,
+                     newton_tol: float = 0.0, newton_maxit: int = 0, step_limit: int = 0,
+                     start_year: int = 0) -> EnsembleResult:
+    """Array form for large ensembles (no per-member Python objects): ``forc[nmem, 10]`` (``Forcing.row()`` layout),
+    ``par[nmem, 15 | 22]`` in ``CLASSIC_PAR_ORDER`` / ``MIZ_PAR_ORDER``, ``state`` a dict of ``[nmem, nx]`` arrays
+    (classic ``E, Tg``; MIZ ``Ei, Ew, h, D, phi`` and optionally the closure warm start ``T0``) -- exactly the buffers
+    of ``ebm_classic_run`` / ``ebm_miz_run`` (include/ebm_cuda.h)."""
+    name = model_name(model)
     lib = _lib.load()
     nx, nt, dur = st.nx, st.nt, st.dur
+    npar = len(CLASSIC_PAR_ORDER) if name == "Classic" else len(MIZ_PAR_ORDER)
+    par = np.ascontiguousarray(par, dtype=np.float64)
+    forc = np.ascontiguousarray(forc, dtype=np.float64)
+    if par.ndim != 2 or par.shape[1] != npar or par.shape[0] == 0:
+        raise ValueError(f"par must be [nmem, {npar}]")
+    nmem = par.shape[0]
+    if forc.shape != (nmem, _lib.NFORCING):
+        raise ValueError(f"forc must be [nmem, {_lib.NFORCING}] (Forcing.row() layout)")
+    keys = _CLASSIC_STATE if name == "Classic" else _MIZ_STATE
+    arrs = {}
+    for k in keys + (("T0",) if (name == "MIZ" and "T0" in state) else ()):
+        if k not in state:
+            raise KeyError(f"initial state lacks {k!r}")
+        a = np.ascontiguousarray(state[k], dtype=np.float64)
+        if a.shape != (nmem, nx):
+            raise ValueError(f"init.{k} must have length nx={nx}")
+        arrs[k] = a
     grid = _lib.make_grid(st)
     opt = _lib.make_options(device, lastonly, field_stride, strict, years_per_launch, newton_maxit, newton_tol,
                             step_limit, start_year)
-    forc = np.ascontiguousarray(np.stack([f.row() for f in forcings]))
     nsel = (nmem + field_stride - 1) // field_stride if field_stride > 0 else 0
     nraw = nt if lastonly else nt * dur
     if want_seasonal is None:
@@ -113,17 +149,12 @@ def integrate_ensemble(model, st: SpaceTime, forcings, pars, inits, *, lastonly:
     res.flags = np.zeros(nmem, dtype=np.int32)
     flags_p = res.flags.ctypes.data_as(C.POINTER(C.c_int32))
     if name == "Classic":
-        par = _rows(pars, CLASSIC_PAR_ORDER)
-        E0, Tg0 = _stack(inits, "E", nx), _stack(inits, "Tg", nx)
         res.final = {"E": np.empty((nmem, nx)), "Tg": np.empty((nmem, nx))}
         out = _lib.ClassicOutputs(_lib.dptr(res.diag), _lib.dptr(res.seasonal), _lib.dptr(res.raw),
                                   _lib.dptr(res.final["E"]), _lib.dptr(res.final["Tg"]), flags_p)
-        _lib.check(lib.ebm_classic_run(C.byref(grid), nmem, _lib.dptr(par), _lib.dptr(forc), _lib.dptr(E0), _lib.dptr(Tg0),
-                                       C.byref(opt), C.byref(out)))
+        _lib.check(lib.ebm_classic_run(C.byref(grid), nmem, _lib.dptr(par), _lib.dptr(forc), _lib.dptr(arrs["E"]),
+                                       _lib.dptr(arrs["Tg"]), C.byref(opt), C.byref(out)))
     else:
-        par = _rows(pars, MIZ_PAR_ORDER)
-        init = [_stack(inits, k, nx) for k in _MIZ_STATE]
-        t0 = None if T0guess is None else np.ascontiguousarray(np.asarray(T0guess, dtype=np.float64).reshape(nmem, nx))
         res.final = {k: np.empty((nmem, nx)) for k in _MIZ_STATE + ("T0",)}
         res.newton_iters = np.zeros(nmem, dtype=np.int64)
         res.nonconv = np.zeros(nmem, dtype=np.int64)
@@ -131,8 +162,8 @@ def integrate_ensemble(model, st: SpaceTime, forcings, pars, inits, *, lastonly:
                               *[_lib.dptr(res.final[k]) for k in _MIZ_STATE + ("T0",)],
                               res.newton_iters.ctypes.data_as(C.POINTER(C.c_int64)),
                               res.nonconv.ctypes.data_as(C.POINTER(C.c_int64)), flags_p)
-        _lib.check(lib.ebm_miz_run(C.byref(grid), nmem, _lib.dptr(par), _lib.dptr(forc), *[_lib.dptr(a) for a in init],
-                                   _lib.dptr(t0), C.byref(opt), C.byref(out)))
+        _lib.check(lib.ebm_miz_run(C.byref(grid), nmem, _lib.dptr(par), _lib.dptr(forc), *[_lib.dptr(arrs[k]) for k in _MIZ_STATE],
+                                   _lib.dptr(arrs.get("T0")), C.byref(opt), C.byref(out)))
     return res
 
 
@@ -143,8 +174,8 @@ def integrate(model, st: SpaceTime, forcing: Forcing, par: Collection, init: Col
     Same arguments as src/infrastructure.jl:615-618.  ``verbose`` prints the closure's non-convergence count
     (the reference @warns per step, src/miz.jl:61-63).
     """
-    res = integrate_ensemble(model, st, [forcing], [par], [init], lastonly=lastonly, field_stride=1, want_diag=False,
-                             device=device, strict=strict, debug=debug)
+    res = integrate_ensemble(model, st, [forcing], [par], [init], debug=debug, lastonly=lastonly, field_stride=1,
+                             want_diag=False, device=device, strict=strict)
     if verbose and res.nonconv is not None and res.nonconv[0] > 0:
         print(f"Warning: solving for T0 failed at {int(res.nonconv[0])} time steps.")
     sols = res.solutions(0, forcing, par, init, lastonly)

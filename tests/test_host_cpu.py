@@ -137,6 +137,22 @@ def test_argument_validation_mirrors_the_reference():
     assert lib.ebm_classic_run(C.byref(g), 1, _lib.dptr(a), _lib.dptr(a), _lib.dptr(a), _lib.dptr(a), None, C.byref(out)) == _lib.EBM_ERR_INVALID
 
 
+def test_integrate_arrays_validates_shapes():
+    st = ebm.SpaceTime(100, 2000, 1)
+    par = np.tile([ebm.default_parameters("Classic")[k] for k in ebm.CLASSIC_PAR_ORDER], (4, 1))
+    forc = np.zeros((4, 10)); z = np.zeros((4, 100))
+    with pytest.raises(ValueError):
+        ebm.integrate_arrays("Classic", st, forc, par[:, :14], {"E": z, "Tg": z})
+    with pytest.raises(ValueError):
+        ebm.integrate_arrays("Classic", st, forc[:3], par, {"E": z, "Tg": z})
+    with pytest.raises(KeyError):
+        ebm.integrate_arrays("Classic", st, forc, par, {"E": z})
+    with pytest.raises(ValueError):
+        ebm.integrate_arrays("Classic", st, forc, par, {"E": z, "Tg": z[:, :99]})
+    with pytest.raises(ValueError):
+        ebm.integrate_arrays("MIZ", st, forc, par, {"E": z, "Tg": z})      # 15 columns are not the 22 MIZ parameters
+
+
 def test_solutions_assembly_layout():
     st = ebm.SpaceTime(50, 100, 3)
     res = ebm.EnsembleResult("Classic", st, 4, 2, ebm.CLASSIC_VARS)
