@@ -106,8 +106,8 @@ __device__ __forceinline__ double ebm_global_time(long long tinx, int nt) {
   return __ddiv_rn((double)(2 * tinx - 1), (double)(2LL * nt));
 }
 
-// Do the members of the 32-aligned group that contains this CTA's members share all classic parameters bit for
-// bit?  Called by every thread of the CTA (contains a barrier); mi = member slot of the thread, MW = members per
+// Do the members of the 32-aligned group that contains this CTA's members share the table-building classic
+// parameters bit for bit?  Called by every thread of the CTA (contains a barrier); mi = member slot of the thread, MW = members per
 // CTA (a divisor of 32).  The uniform and the general kernel use this same rule to split an ensemble between them.
 template <int MW>
 __device__ __forceinline__ bool ebm_classic_group_uniform(const double* __restrict__ par, long long nmem,
@@ -118,8 +118,13 @@ __device__ __forceinline__ bool ebm_classic_group_uniform(const double* __restri
   for (int r = 0; r < 32 / MW; ++r) {
     long long mm = g0 + mi + (long long)r * MW;
     if (mm >= nmem) mm = nmem - 1;
-    for (int k = 0; k < EBM_CLASSIC_NPAR; ++k)
+    // only the parameters that feed the CTA-wide tables must agree: D, cg, tau (the matrix kappa, classic.jl:21) and
+    // S0, S2, a0, a2 (insolation / albedo profiles, :23-28); A, B, cw, S1, ai, Fb, k, Lf are per-member registers
+    constexpr int kTablePar[7] = {0, 4, 6, 7, 8, 13, 14};
+    for (int q = 0; q < 7; ++q) {
+      const int k = kTablePar[q];
       same = same && (par[(long long)k * nmem + mm] == par[(long long)k * nmem + g0]);
+    }
   }
   return __syncthreads_and(same) != 0;
 }

@@ -199,3 +199,24 @@ def test_c4_members_two_hundred_years():
     # the sample covers both ends of the hysteresis loop: a nearly ice-free warm-branch member and snowball members
     area = r.diag[:, -1, 2, 2]
     assert area.min() < 0.5 and area.max() > 6.0
+
+
+def test_sweep_of_non_matrix_parameters_takes_the_table_driven_kernel():
+    """A, B, cw, S1, ai, Fb, k, Lf may differ per member inside a 32-member group of the fast (table-driven) kernel --
+    only D, cg, tau, S0, S2, a0, a2 build its shared tables.  70 members sweeping B, A, ai, k and the forcing."""
+    nmem, nx = 70, 100
+    st = ebm.SpaceTime(nx, 2000, 3)
+    forcings = [ebm.Forcing(-6.0 + 12.0 * (m % 9) / 8.0) for m in range(nmem)]
+    pars = [_par(B=1.9 + 0.05 * (m % 6), A=190.0 + (m % 4), ai=0.38 + 0.01 * (m % 5), k=1.8 + 0.1 * (m % 3)) for m in range(nmem)]
+    inits = [warm_init(nx) if m % 2 == 0 else cold_init(nx) for m in range(nmem)]
+    o = oracle_classic(st, forcings, pars, inits, raw=True, seasonal=True)
+    lib = ebm._lib.load()
+    n0 = lib.ebm_launch_count()
+    r = ebm.integrate_ensemble("Classic", st, forcings, pars, inits, field_stride=5)
+    assert lib.ebm_launch_count() > n0 and r.flags.max() == 0
+    assert_close(r.final["E"], o["E"], TOL, "final E")
+    assert_close(r.final["Tg"], o["Tg"], TOL, "final Tg")
+    sel = np.arange(0, nmem, 5)
+    assert_close(r.raw, o["raw"][sel], TOL, "raw")
+    assert_close(r.seasonal, o["seasonal"][sel], TOL, "seasonal")
+    assert_close(r.diag[..., :2], oracle_diag_classic(o["seasonal"], st.x)[..., :2], TOL, "diag")
