@@ -6,7 +6,10 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
+#include <array>
 #include <atomic>
+#include <map>
 #include <mutex>
 #include <vector>
 
@@ -300,20 +303,37 @@ extern "C" int32_t ebm_classic_run(const ebm_grid_t* grid, int64_t nmem, const e
   std::vector<long long> perm;
   long long* dperm = nullptr;
   if (!opt.strict && nmem > 32 && !getenv("EBM_NO_REORDER")) {
-    std::vector<unsigned char> key((size_t)nmem);
-    bool sorted = true;
+    // primary key: the set of table-building parameters (D, S0, S2, a0, a2, cg, tau -- the table-driven kernel needs
+    // them uniform over 32-member groups), numbered in order of first appearance; secondary: regime of the initial
+    // state (0 ice free, 1 partial cover, 2 every cell ice).  Ensembles made of many distinct parameter sets
+    // (a pure sweep over D) are left in the caller's order within each regime.
+    static const int kTablePar[7] = {0, 4, 6, 7, 8, 13, 14};
+    std::map<std::array<double, 7>, int> sets;
+    std::vector<int> key((size_t)nmem);
+    const double* prow = (const double*)par;
+    bool many_sets = false;
     for (long long m = 0; m < nmem; ++m) {
       int ice = 0;
       for (int j = 0; j < nx; ++j) ice += E0[m * nx + j] < 0.0;
-      key[m] = ice == 0 ? 0 : (ice == nx ? 2 : 1);        // 0 ice free, 1 partial cover, 2 every cell ice
-      if (m > 0 && key[m] < key[m - 1]) sorted = false;
+      const int regime = ice == 0 ? 0 : (ice == nx ? 2 : 1);
+      int sid = 0;
+      if (!many_sets) {
+        std::array<double, 7> tp;
+        for (int q = 0; q < 7; ++q) tp[q] = prow[m * EBM_CLASSIC_NPAR + kTablePar[q]];
+        auto it = sets.find(tp);
+        if (it == sets.end()) it = sets.emplace(tp, (int)sets.size()).first;
+        sid = it->second;
+        if ((long long)sets.size() * 32 > nmem) many_sets = true;   // groups cannot be made uniform anyway
+      }
+      key[m] = sid * 4 + regime;
     }
+    if (many_sets) for (long long m = 0; m < nmem; ++m) key[m] &= 3;
+    bool sorted = true;
+    for (long long m = 1; m < nmem; ++m) if (key[m] < key[m - 1]) { sorted = false; break; }
     if (!sorted) {
       perm.resize((size_t)nmem);
-      long long pos = 0;
-      for (int k = 0; k < 3; ++k)
-        for (long long m = 0; m < nmem; ++m)
-          if (key[m] == k) perm[pos++] = m;               // perm[slot] = original index
+      for (long long m = 0; m < nmem; ++m) perm[m] = m;
+      std::stable_sort(perm.begin(), perm.end(), [&](long long a, long long b) { return key[a] < key[b]; });   // perm[slot] = original index
       EBM_TRY(B.alloc(&dperm, (size_t)nmem));
       EBM_CUDA_TRY(cudaMemcpyAsync(dperm, perm.data(), sizeof(long long) * nmem, cudaMemcpyHostToDevice, s));
     }
