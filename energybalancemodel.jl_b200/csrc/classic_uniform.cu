@@ -627,19 +627,14 @@ extern "C" int ebm_debug_phase_cycles(unsigned long long* out64) {
 int ebm_launch_classic_uniform(const ClassicKArgs& a, int variant, cudaStream_t stream) {
   if (a.nx > ebm_classic_uniform_max_nx()) return EBM_OK;   // larger grids: the general kernel integrates every group
   switch (variant) {
-    // <K cells/thread, WB bands, MW members/CTA, max registers/thread>
-    case 1: return launch_uniform<13, 8, 16, 168>(a, stream);   // 3 warps / sub-partition: 3 CTAs per SM
-    case 2: return launch_uniform<13, 8, 16, 128>(a, stream);   // 4 warps / sub-partition: 4 CTAs per SM (spills)
-    case 3: return launch_uniform<7, 16, 16, 128>(a, stream);   // 8 warps per CTA, 2 CTAs per SM
-    case 4: return launch_uniform<7, 16, 16, 96>(a, stream);
-    case 5: return launch_uniform<13, 8, 16, 255>(a, stream);         // band rows in registers: 2 CTAs per SM
-    case 6: return launch_uniform<13, 8, 16, 128, true>(a, stream);   // band rows in shared memory, 128 registers (spills)
-    case 7: return launch_uniform<13, 8, 16, 255, true>(a, stream);
-    case 8: return launch_uniform<7, 16, 16, 128, true>(a, stream);   // 16 bands of 7 cells, 8 warps per CTA, 2 CTAs per SM
-    case 9: return launch_uniform<13, 8, 16, 168, true, true>(a, stream);   // member-in-warp mapping, no CTA barrier
-    case 10: return launch_uniform<13, 8, 16, 255, true, true>(a, stream);
-    // default: band rows (pivots / spikes) in thread-private shared memory, 168 registers -> 3 CTAs (12 warps) per SM:
-    // fastest measured at 65 536 members (826 k member-years/s vs 734 k with the rows in registers at 2 CTAs per SM)
+    // <K cells/thread, WB bands, MW members/CTA, max registers/thread, band rows in smem, member-in-warp mapping>
+    // measured at 65 536 members x 20 years (member-years/s); the rejected ones stay selectable for re-measurement
+    case 5: return launch_uniform<13, 8, 16, 255>(a, stream);               // rows in registers, 2 CTAs/SM:   735 k
+    case 7: return launch_uniform<13, 8, 16, 255, true>(a, stream);         // rows in smem, 2 CTAs/SM:         704 k
+    case 8: return launch_uniform<7, 16, 16, 128, true>(a, stream);         // 16 bands of 7 cells, 16 warps/SM: 583 k
+    case 9: return launch_uniform<13, 8, 16, 168, true, true>(a, stream);   // member-in-warp, no CTA barrier:   717 k
+    // default: band rows (pivots / spikes / carried reciprocals) in thread-private shared memory, 168 registers,
+    // 3 CTAs (12 warps) per SM: 921 k
     default: return launch_uniform<13, 8, 16, 168, true>(a, stream);
   }
 }
