@@ -80,12 +80,28 @@ struct RowStore {
   }
 };
 
-template <int K, int WB, int MW, bool QS_SMEM, bool WARPM>
+template <int K, int WB, int MW, bool QS_SMEM, bool WARPM, bool TAB>
 struct Ctx {
   static constexpr int NXP = K * WB;
   // tables / scratch in shared memory
   const PhysTab* phys; const ElimTab* elim; const CoefTab* coef; const double* bandc;
   double *iface, *zs, *red, *sumT, *sumH;
+  // TAB = false (groups whose table-building parameters differ between members): the shared tables hold geometry
+  // only and every thread applies its own member's S0, S2, a0, a2 and fac = dt*D/cg on the fly; all rows take the
+  // general elimination (no precomputed pivots)
+  double S0m, S2m, a0m, a2m, facm, fac2m, one_dttaum;
+  __device__ __forceinline__ PhysTab phys_at(int j) const {
+    PhysTab p = phys[j];
+    if constexpr (!TAB) { p.S0x = fma(-S2m, p.S0x, S0m); p.aw = fma(-a2m, p.aw, a0m); }   // the table holds x^2 in both slots
+    return p;
+  }
+  __device__ __forceinline__ CoefTab coef_at(int j) const {
+    CoefTab c = coef[j];
+    if constexpr (!TAB) {   // the table holds lam_lo + lam_hi, lam_lo, lam_hi, lam_lo_j * lam_hi_{j-1}
+      c.kjj = fma(facm, c.kjj, one_dttaum); c.aoff = -facm * c.aoff; c.coff = -facm * c.coff; c.ac = fac2m * c.ac;
+    }
+    return c;
+  }
   // member constants
   double A, Fb, ai, cg_tau, M, kLf, inv_cw, dt, dt_tau, dttau_cw, dc, inv_nt, inv_Lf;
   // thread identity
@@ -151,7 +167,7 @@ struct Ctx {
     const double fmAFb = fmA + Fb;
     const int season = SLOW ? ((ti == a.winter_inx) ? 0 : (ti == a.summer_inx) ? 1 : (ti == nt) ? 2 : -1) : -1;
     // rs.q(i): diagonal decrement dc/(M - kLf/E) of a masked row (else 0); later the pivots / spikes of the band
-    bool anymask = false;
+    bool anymask = !TAB;   // without precomputed pivots every band eliminates in full
     PHASE_BEGIN();
     double dgT = 0.0, dgE = 0.0, dgA = 0.0, dgX = 2.0;
 
@@ -166,7 +182,7 @@ struct Ctx {
       for (int i = 0; i < K; ++i) se[i] = sumE[cidx(i)];
 #pragma unroll
       for (int i = 0; i < K; ++i) {
-        const PhysTab p = phys[j0 + i];
+        const PhysTab p = phys_at(j0 + i);
         const double S = fma(-S1c0, p.S1x, p.S0x);          // S[j,i]; S1x holds x_j, S0x = S0 - S2 x_j^2
         const double Eo = E[i], Tgo = Tg[i];
         const double alpha = is_zero(Eo) ? 0.0 : p.aw;      // alpha = aw, or 0 at E == 0                 :47
@@ -175,6 +191,7 @@ struct Ctx {
         const double En = fma(dt, fma(-M, T, Cb), Eo);                                            //     :53
         E[i] = En;
         Tg[i] = fma(dttau_cw, En, Tgo);
+        if constexpr (!TAB) rs.q(i) = 0.0;
         crossed = crossed || is_neg(En);
         sample<SLOW>(a, i, p.wts, En, T, season, ti, year, se[i], dgT, dgE, dgA, dgX);
       }
@@ -188,7 +205,7 @@ struct Ctx {
           const double En = E[i];
           if (is_neg(En)) {
             // recover the old state of this cell from the update formulas (only the sign of T0 is needed)
-            const PhysTab p = phys[j0 + i];
+            const PhysTab p = phys_at(j0 + i);
             const double Tgo = fma(-dttau_cw, En, Tg[i]);
             const double Cb = fma(p.aw, fma(-S1c0, p.S1x, p.S0x), fma(cg_tau, Tgo, fmAFb));
             const double Eo = fma(-dt, Cb, En) / fma(-dt * M, inv_cw, 1.0);
@@ -211,7 +228,7 @@ struct Ctx {
       for (int i = 0; i < K; ++i) { rv[i] = rs.r(i); se[i] = sumE[cidx(i)]; }
 #pragma unroll
       for (int i = 0; i < K; ++i) {
-        const PhysTab p = phys[j0 + i];
+        const PhysTab p = phys_at(j0 + i);
         const double S = fma(-S1c0, p.S1x, p.S0x);
         const double Eo = E[i], Tgo = Tg[i];
         const bool ice = is_neg(Eo);
@@ -265,7 +282,7 @@ struct Ctx {
       double Pm2 = 1.0, Pm1 = 1.0;
 #pragma unroll
       for (int i = 0; i < K; ++i) {
-        const CoefTab cf = coef[j0 + i];
+        const CoefTab cf = coef_at(j0 + i);
         const double diag = cf.kjj - rs.q(i);
         const double P = (i == 0) ? diag : fma(diag, Pm1, -(cf.ac * Pm2));
         rs.s(i) = Pm1 * fast_rcp(P);            // 1 / w_i
@@ -274,7 +291,7 @@ struct Ctx {
       double yprev = 0.0, sprev = 0.0;
 #pragma unroll
       for (int i = 0; i < K; ++i) {
-        const CoefTab cf = coef[j0 + i];
+        const CoefTab cf = coef_at(j0 + i);
         const double iw = rs.s(i);
         const double tq = cf.aoff * iw;
         const double yi = (i == 0) ? Tg[i] * iw : fma(-tq, yprev, Tg[i] * iw);
@@ -434,7 +451,7 @@ constexpr size_t uniform_smem_bytes(bool fields) {
                            (QS_SMEM ? (size_t)3 * K * WB * MW : 0));
 }
 
-template <int K, int WB, int MW, int MAXR, bool QS_SMEM, bool WARPM>
+template <int K, int WB, int MW, int MAXR, bool QS_SMEM, bool WARPM, bool TAB>
 __global__ void __maxnreg__(MAXR) classic_uniform_kernel(const ClassicKArgs a) {
   static_assert(MW == 16, "warp 0 = two lanes per member (full-warp shuffles)");
   static_assert(!WARPM || (32 % WB == 0 && QS_SMEM), "member-in-warp mapping: WB bands x 32/WB members per warp");
@@ -455,7 +472,8 @@ __global__ void __maxnreg__(MAXR) classic_uniform_kernel(const ClassicKArgs a) {
   const long long m = active ? m_raw : nmem - 1;
   const int nx = a.nx, nt = a.nt;
 
-  if (!ebm_classic_group_uniform<MW>(a.par, nmem, m_first, mi)) return;   // classic_bands.cu integrates this group
+  // the TAB instance integrates the 32-member groups whose table-building parameters agree, the !TAB instance the rest
+  if (ebm_classic_group_uniform<MW>(a.par, nmem, m_first, mi) != TAB) return;
   double par[EBM_CLASSIC_NPAR];
 #pragma unroll
   for (int k = 0; k < EBM_CLASSIC_NPAR; ++k) par[k] = a.par[(long long)k * nmem + m];
@@ -486,10 +504,17 @@ __global__ void __maxnreg__(MAXR) classic_uniform_kernel(const ClassicKArgs a) {
     const bool v = j < nx;
     const double xj = v ? a.g.x[j] : 0.0, x2 = v ? a.g.x2[j] : 0.0;
     const double ll = v ? a.g.lam_lo[j] : 0.0, lh = v ? a.g.lam_hi[j] : 0.0;
-    PhysTab p; p.S0x = fma(-pS2, x2, pS0); p.S1x = xj; p.aw = fma(-pa2, x2, pa0); p.wts = v ? a.g.wts[j] : 0.0;
+    PhysTab p; CoefTab c;
+    const double lhm = (j % K == 0 || !v) ? 0.0 : a.g.lam_hi[j - 1];
+    if constexpr (TAB) {
+      p.S0x = fma(-pS2, x2, pS0); p.aw = fma(-pa2, x2, pa0);
+      c.kjj = fma(fac, ll + lh, one_dttau); c.aoff = -fac * ll; c.coff = -fac * lh; c.ac = c.aoff * (-fac * lhm);
+    } else {   // geometry only: Ctx::phys_at / coef_at apply the member's parameters
+      p.S0x = x2; p.aw = x2;
+      c.kjj = ll + lh; c.aoff = ll; c.coff = lh; c.ac = ll * lhm;
+    }
+    p.S1x = xj; p.wts = v ? a.g.wts[j] : 0.0;
     phys[j] = p;
-    CoefTab c; c.kjj = fma(fac, ll + lh, one_dttau); c.aoff = -fac * ll; c.coff = -fac * lh;
-    c.ac = (j % K == 0) ? 0.0 : c.aoff * (-fac * (v ? a.g.lam_hi[j - 1] : 0.0));
     coef[j] = c;
   }
   for (int qd = tid; qd < 6 * MW; qd += blockDim.x) iface[WB * 6 * MW + qd] = 0.0;
@@ -501,7 +526,7 @@ __global__ void __maxnreg__(MAXR) classic_uniform_kernel(const ClassicKArgs a) {
   }
   __syncthreads();
   // band-local elimination of the constant matrix kappa (no masked rows)
-  if (tid < WB) {
+  if (TAB && tid < WB) {
     const int b = tid;
     double qprev = 0.0, sprev = 0.0;
     for (int i = 0; i < K; ++i) {
@@ -520,7 +545,8 @@ __global__ void __maxnreg__(MAXR) classic_uniform_kernel(const ClassicKArgs a) {
     bandc[2 * b] = be; bandc[2 * b + 1] = ga;
   }
 
-  Ctx<K, WB, MW, QS_SMEM, WARPM> cx;
+  Ctx<K, WB, MW, QS_SMEM, WARPM, TAB> cx;
+  cx.S0m = pS0; cx.S2m = pS2; cx.a0m = pa0; cx.a2m = pa2; cx.facm = fac; cx.fac2m = fac * fac; cx.one_dttaum = one_dttau;
   cx.rs.base = qsm + tid;
   cx.rs.stride = WB * MW;
   cx.phys = phys; cx.elim = elim; cx.coef = coef; cx.bandc = bandc;
@@ -587,7 +613,7 @@ __global__ void __maxnreg__(MAXR) classic_uniform_kernel(const ClassicKArgs a) {
   if (bad && a.flags != nullptr) atomicOr(a.flags + mo, 1);
 }
 
-template <int K, int WB, int MW, int MAXR, bool QS_SMEM = false, bool WARPM = false>
+template <int K, int WB, int MW, int MAXR, bool QS_SMEM = false, bool WARPM = false, bool TAB = true>
 int launch_uniform(const ClassicKArgs& a, cudaStream_t stream) {
   if (a.nx > K * WB) {
     ebm_set_error("classic_uniform: nx=%d exceeds %d bands of %d cells", a.nx, WB, K);
@@ -595,7 +621,7 @@ int launch_uniform(const ClassicKArgs& a, cudaStream_t stream) {
   }
   const bool fields = a.seasonal != nullptr && a.field_stride > 0;
   const size_t smem = uniform_smem_bytes<K, WB, MW, QS_SMEM>(fields);
-  auto kern = classic_uniform_kernel<K, WB, MW, MAXR, QS_SMEM, WARPM>;
+  auto kern = classic_uniform_kernel<K, WB, MW, MAXR, QS_SMEM, WARPM, TAB>;
   EBM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // leave room for several CTAs per SM: ask for the largest shared-memory carve-out (L1 is hardly used)
   EBM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -609,6 +635,13 @@ int launch_uniform(const ClassicKArgs& a, cudaStream_t stream) {
 }  // namespace
 
 int ebm_classic_uniform_max_nx() { return 104; }
+
+// groups whose table-building parameters differ between members (e.g. a sweep over D): same mapping, coefficients
+// applied per member, every band eliminated in full
+int ebm_launch_classic_general(const ClassicKArgs& a, cudaStream_t stream) {
+  if (a.nx > ebm_classic_uniform_max_nx()) return EBM_OK;
+  return launch_uniform<13, 8, 16, 168, true, false, false>(a, stream);
+}
 
 // dev: read and reset the phase counters (zeros unless built with -DEBM_PHASE_TIMING)
 extern "C" int ebm_debug_phase_cycles(unsigned long long* out64) {

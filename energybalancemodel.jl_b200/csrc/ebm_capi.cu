@@ -266,9 +266,16 @@ extern "C" int32_t ebm_classic_run_device(const ebm_grid_t* grid, const ebm_clas
     } else {
       // parameter-uniform 32-member groups take the table-driven kernel, everything else the general one
       static const int variant = getenv("EBM_CLASSIC_VARIANT") ? atoi(getenv("EBM_CLASSIC_VARIANT")) : 0;
+      // nx <= 104: the table-driven kernel takes the 32-member groups whose table-building parameters agree, its
+      // per-member-coefficient instance the others; larger grids (or EBM_CLASSIC_VARIANT < 0): the band kernel
       a.uniform_split = (a.nx <= ebm_classic_uniform_max_nx() && variant >= 0) ? 1 : 0;
-      if (a.uniform_split) EBM_TRY(ebm_launch_classic_uniform(a, variant, stream));
-      EBM_TRY(ebm_launch_classic_bands(a, stream));
+      if (a.uniform_split) {
+        EBM_TRY(ebm_launch_classic_uniform(a, variant, stream));
+        if (variant == 11) EBM_TRY(ebm_launch_classic_bands(a, stream));   // previous split, kept for comparison
+        else EBM_TRY(ebm_launch_classic_general(a, stream));
+      } else {
+        EBM_TRY(ebm_launch_classic_bands(a, stream));
+      }
     }
   }
   return EBM_OK;

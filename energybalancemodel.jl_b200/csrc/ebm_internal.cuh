@@ -73,6 +73,7 @@ struct MizKArgs {
 // launchers (each returns an EBM_* status; kernels are enqueued on `stream`)
 int ebm_launch_classic_bands(const ClassicKArgs& a, cudaStream_t stream);
 int ebm_launch_classic_uniform(const ClassicKArgs& a, int variant, cudaStream_t stream);
+int ebm_launch_classic_general(const ClassicKArgs& a, cudaStream_t stream);
 int ebm_classic_uniform_max_nx();
 int ebm_launch_classic_strict(const ClassicKArgs& a, cudaStream_t stream);
 int ebm_launch_classic_single_step(const EbmGridTables& g, const double* par15, int ti, double f,
