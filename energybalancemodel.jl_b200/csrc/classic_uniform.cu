@@ -634,12 +634,13 @@ int launch_uniform(const ClassicKArgs& a, cudaStream_t stream) {
 
 }  // namespace
 
-int ebm_classic_uniform_max_nx() { return 104; }
+int ebm_classic_uniform_max_nx() { return 208; }   // 8 bands of 13 cells up to nx = 104, 16 bands up to 208
 
 // groups whose table-building parameters differ between members (e.g. a sweep over D): same mapping, coefficients
 // applied per member, every band eliminated in full
 int ebm_launch_classic_general(const ClassicKArgs& a, cudaStream_t stream) {
   if (a.nx > ebm_classic_uniform_max_nx()) return EBM_OK;
+  if (a.nx > 104) return launch_uniform<13, 16, 16, 255, true, false, false>(a, stream);
   return launch_uniform<13, 8, 16, 168, true, false, false>(a, stream);
 }
 
@@ -658,7 +659,8 @@ extern "C" int ebm_debug_phase_cycles(unsigned long long* out64) {
 
 // variant: 0 = default.  Other values select alternative instantiations for tuning (env EBM_CLASSIC_VARIANT).
 int ebm_launch_classic_uniform(const ClassicKArgs& a, int variant, cudaStream_t stream) {
-  if (a.nx > ebm_classic_uniform_max_nx()) return EBM_OK;   // larger grids: the general kernel integrates every group
+  if (a.nx > ebm_classic_uniform_max_nx()) return EBM_OK;   // larger grids: the band kernel integrates every group
+  if (a.nx > 104) return launch_uniform<13, 16, 16, 255, true>(a, stream);   // 16 bands, 8 warps per CTA, 1 CTA per SM
   switch (variant) {
     // <K cells/thread, WB bands, MW members/CTA, max registers/thread, band rows in smem, member-in-warp mapping>
     // measured at 65 536 members x 20 years (member-years/s); the rejected ones stay selectable for re-measurement
