@@ -106,12 +106,16 @@ __device__ __forceinline__ void diffuse(const double* __restrict__ lo, const dou
                                         const double (&tb)[K], double (&out)[K]) {
   const double left = shfl_up1(tb[K - 1]);
   const double right = shfl_dn1(tb[0]);
+  // d[i] = T[j] - T[j-1] for the lane's cells, d[K] towards the next lane: each difference serves two cells
+  double d[K + 1];
+  d[0] = tb[0] - left;
+#pragma unroll
+  for (int i = 1; i < K; ++i) d[i] = tb[i] - tb[i - 1];
+  d[K] = right - tb[K - 1];
 #pragma unroll
   for (int i = 0; i < K; ++i) {
     const int s = i * 32 + lane;
-    const double tm = (i == 0) ? left : tb[i - 1];
-    const double tp = (i == K - 1) ? right : tb[i + 1];
-    out[i] = fma(up[s], tp - tb[i], -lo[s] * (tb[i] - tm));   // a zero coefficient silences the missing neighbour
+    out[i] = fma(up[s], d[i + 1], -lo[s] * d[i]);   // a zero coefficient silences the missing neighbour
   }
 }
 

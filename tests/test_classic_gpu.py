@@ -241,3 +241,39 @@ def test_interleaved_parameter_sets_are_regrouped():
     assert_close(r.raw, o["raw"][sel], TOL, "raw")
     assert_close(r.seasonal, o["seasonal"][sel], TOL, "seasonal")
     assert_close(r.diag[..., :2], oracle_diag_classic(o["seasonal"], st.x)[..., :2], TOL, "diag")
+
+
+def test_device_entry_point_with_member_index():
+    """ebm_classic_run_device (inputs resident in HBM, torch tensors as the allocator): the members are handed over
+    in a shuffled order with member_index = original index of each slot; diagnostics and flags land at the original
+    rows, and every member's result equals the host entry point's bit for bit (members are independent)."""
+    import ctypes as C
+    import torch
+    from ebm_b200 import _lib
+    nmem, nx, years = 96, 100, 2
+    st = ebm.SpaceTime(nx, 2000, years)
+    p = _par()
+    par = np.tile([p[k] for k in ebm.CLASSIC_PAR_ORDER], (nmem, 1))
+    forc = np.zeros((nmem, 10)); forc[:, :3] = np.linspace(-12.0, 12.0, nmem)[:, None]
+    warm = (np.arange(nmem) % 3) != 0
+    state = {"E": np.where(warm[:, None], 98.0, -9.5) * np.ones((nmem, nx)), "Tg": np.where(warm[:, None], 10.0, -10.0) * np.ones((nmem, nx))}
+    ref = ebm.integrate_arrays("Classic", st, forc, par, state)
+    perm = np.random.default_rng(5).permutation(nmem)                      # slot -> original index
+    dev = torch.device("cuda", 0)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    d_par, d_forc = t(par[perm].T), t(forc[perm].T)
+    d_E, d_Tg = t(state["E"][perm].T), t(state["Tg"][perm].T)
+    d_diag = torch.full((nmem, years, 3, 4), float("nan"), dtype=torch.float64, device=dev)
+    d_flags = torch.zeros(nmem, dtype=torch.int32, device=dev)
+    d_idx = t(perm.astype(np.int64))
+    lib = _lib.load()
+    grid, opt = _lib.make_grid(st), _lib.make_options(device=0)
+    args = _lib.ClassicDeviceArgs(nmem, d_par.data_ptr(), d_forc.data_ptr(), d_E.data_ptr(), d_Tg.data_ptr(),
+                                  d_diag.data_ptr(), None, None, d_flags.data_ptr(), d_idx.data_ptr())
+    _lib.check(lib.ebm_classic_run_device(C.byref(grid), C.byref(args), C.byref(opt), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    torch.cuda.synchronize()
+    assert np.array_equal(d_diag.cpu().numpy(), ref.diag)                  # rows at the original member index
+    assert int(d_flags.max().item()) == 0
+    E_fin = np.empty((nmem, nx)); E_fin[perm] = d_E.cpu().numpy().T        # state stays in slot order
+    Tg_fin = np.empty((nmem, nx)); Tg_fin[perm] = d_Tg.cpu().numpy().T
+    assert np.array_equal(E_fin, ref.final["E"]) and np.array_equal(Tg_fin, ref.final["Tg"])
