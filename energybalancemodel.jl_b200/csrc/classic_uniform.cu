@@ -1,23 +1,31 @@
-// classic_uniform.cu -- fast path of the classic EBM ensemble for 32-member groups whose members share all
-// model parameters (forcing and initial state may differ per member: forcing sweeps, hysteresis runs).
+// classic_uniform.cu -- the classic (Wagner-Eisenman) EBM ensemble kernel for grids up to 208 cells.
+//
+// Two instances share this source: TAB = true integrates the 32-member groups whose table-building parameters
+// (D, cg, tau, S0, S2, a0, a2) agree -- forcing sweeps, hysteresis runs, sweeps over A, B, cw, S1, ai, Fb, k, Lf;
+// TAB = false the groups where they differ (coefficients applied per member, no precomputed pivots).
 //
 // Mapping (B200 facts measured with scripts/microbench/fp64_lat.cu: DFMA latency 8.8 cycles, one warp can issue
 // a DFMA every 2.4 cycles, the 64 KB register file of an SM sub-partition holds 3 warps at <=168 registers):
-//   * lane = member, warp = 2 latitude bands of K cells for 16 members; CTA = 16 members x WB=8 bands = 4 warps,
-//     one per SM sub-partition; 3 CTAs per SM.  E and Tg of every cell stay in registers for the whole launch.
+//   * lane = member, warp = 2 latitude bands of K = 13 cells for 16 members; CTA = 16 members x WB = 8 bands =
+//     4 warps, one per SM sub-partition; 3 CTAs per SM (168 registers; 74.9 KB of shared memory per CTA).
+//     E and Tg of every cell stay in registers for the whole launch.  (Measured and rejected: all bands of a
+//     member in one warp, 4 bands per warp, 16 bands of 7 cells -- band-homogeneous warps win)
 //   * every latitude-dependent coefficient (S0-S2x^2, x, a0-a2x^2, kappa) is a CTA-wide table in shared memory,
 //     read with broadcast 128-bit loads.
-//   * physics is branch-free per cell (selects), so the K cells of a thread overlap in the FP64 pipe; the one
-//     branch is per thread: "all my cells are open water" (9 FP64 instructions per cell) or not.
+//   * physics per cell with selects; the one branch is per thread: "all my cells are open water" (9 FP64
+//     instructions per cell) or not.  1/(M - kLf/E) of every cell is carried from step to step.
 //   * implicit ghost-layer solve (classic.jl:55-63; symmetric tridiagonal, diagonal depends on the member's
 //     ice mask): partitioned.  Rows whose diagonal is the constant kappa_jj -- open water, or ice with a melting
 //     surface, i.e. mask (T0<0)&(E<0) false -- have member-independent pivots: a band without masked rows uses
 //     elimination tables precomputed once per launch (5 FP64 instructions per row); a band with masked rows
-//     eliminates in full.  The WB x WB interface system is solved by warp 0 from both ends at once with
-//     determinant-form pivots (one dependent DFMA per row) entirely in registers.  Two CTA barriers per step.
+//     eliminates in full with determinant-form pivots (one dependent DFMA per row, independent reciprocals).
+//     The WB x WB interface system is solved by warp 0 from both ends at once, entirely in registers.
+//     Two CTA barriers per step.
+//   * what survives from elimination to back substitution (pivots, spikes), the carried reciprocals and the
+//     per-cell annual sums of E live in thread-private shared memory [row][thread] (conflict free).
 //   * the hot step carries no sampling code; steps that store output and CTAs that own a member with field
-//     output take a second instantiation.  Annual mean of E: registers; annual mean of T: one scalar per thread
-//     (hemispheric mean is linear); per-cell sums of T and h only in CTAs that write fields.
+//     output take a second instantiation.  Annual mean of T: one scalar per thread (hemispheric mean is linear);
+//     per-cell sums of T and h only in CTAs that write fields.
 // Citations: src/classic.jl:43-65 (step), src/infrastructure.jl:549-591 (savesol!), SURVEY.md Appendix A.
 #include "ebm_internal.cuh"
 
