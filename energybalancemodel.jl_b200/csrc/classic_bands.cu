@@ -1,4 +1,6 @@
-// classic_bands.cu -- the hot kernel for the classic (Wagner-Eisenman) EBM ensemble.
+// classic_bands.cu -- band kernel of the classic (Wagner-Eisenman) EBM ensemble: the first fast kernel of this
+// library, now the fallback for grids with 208 < nx <= 256 (and EBM_CLASSIC_VARIANT < 0 / 11 for comparison);
+// classic_uniform.cu integrates everything up to 208 cells 2-3x faster.
 //
 // Replaces, for a whole ensemble and many years per launch, the reference's
 //   integrate loop           src/infrastructure.jl:630-634
