@@ -3,10 +3,13 @@
 
 namespace {
 
-// [rows][cols] -> [cols][rows], 32x32 tiles through shared memory (coalesced on both sides)
-__global__ void transpose_kernel(const double* __restrict__ src, double* __restrict__ dst, long long rows, long long cols) {
+// [rows][cols] -> [cols][rows], 32x32 tiles through shared memory (coalesced on both sides).  The larger tile count
+// goes to gridDim.x (2^31 - 1 blocks), the smaller to gridDim.y (65535): either dimension may be the member axis.
+__global__ void transpose_kernel(const double* __restrict__ src, double* __restrict__ dst, long long rows, long long cols,
+                                 int rows_on_x) {
   __shared__ double tile[32][33];
-  const long long c0 = (long long)blockIdx.x * 32, r0 = (long long)blockIdx.y * 32;
+  const long long r0 = (long long)(rows_on_x ? blockIdx.x : blockIdx.y) * 32;
+  const long long c0 = (long long)(rows_on_x ? blockIdx.y : blockIdx.x) * 32;
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     const long long r = r0 + i, c = c0 + threadIdx.x;
     if (r < rows && c < cols) tile[i][threadIdx.x] = src[r * cols + c];
@@ -54,10 +57,11 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters, 
 
 int ebm_launch_transpose(const double* src, double* dst, long long rows, long long cols, cudaStream_t stream) {
   if (rows <= 0 || cols <= 0) return EBM_OK;
-  dim3 block(32, 8);
-  dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32));
-  if (grid.y > 65535) { ebm_set_error("transpose: too many rows (%lld)", rows); return EBM_ERR_INVALID; }
-  transpose_kernel<<<grid, block, 0, stream>>>(src, dst, rows, cols);
+  const long long tr = (rows + 31) / 32, tc = (cols + 31) / 32;
+  const int rows_on_x = tr >= tc;
+  const long long gx = rows_on_x ? tr : tc, gy = rows_on_x ? tc : tr;
+  if (gx > 0x7fffffffLL || gy > 65535) { ebm_set_error("transpose: %lld x %lld is too large", rows, cols); return EBM_ERR_INVALID; }
+  transpose_kernel<<<dim3((unsigned)gx, (unsigned)gy), dim3(32, 8), 0, stream>>>(src, dst, rows, cols, rows_on_x);
   EBM_CUDA_TRY(cudaGetLastError());
   ebm_count_launch();
   return EBM_OK;

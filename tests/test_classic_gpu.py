@@ -277,3 +277,18 @@ def test_device_entry_point_with_member_index():
     E_fin = np.empty((nmem, nx)); E_fin[perm] = d_E.cpu().numpy().T        # state stays in slot order
     Tg_fin = np.empty((nmem, nx)); Tg_fin[perm] = d_Tg.cpu().numpy().T
     assert np.array_equal(E_fin, ref.final["E"]) and np.array_equal(Tg_fin, ref.final["Tg"])
+
+
+@pytest.mark.parametrize("rows,cols", [(70001, 37), (37, 70001), (1, 5), (2100000, 3)])
+def test_transpose_device_layout_helper(rows, cols):
+    """ebm_transpose_device: [rows][cols] -> [cols][rows] for member counts beyond 65535*32 on either axis."""
+    import ctypes as C
+    import torch
+    from ebm_b200 import _lib
+    lib = _lib.load()
+    src = torch.arange(rows * cols, dtype=torch.float64, device="cuda").reshape(rows, cols)
+    dst = torch.empty((cols, rows), dtype=torch.float64, device="cuda")
+    _lib.check(lib.ebm_transpose_device(C.c_void_p(src.data_ptr()), C.c_void_p(dst.data_ptr()), rows, cols,
+                                        C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    torch.cuda.synchronize()
+    assert torch.equal(dst, src.t().contiguous())
