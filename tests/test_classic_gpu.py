@@ -292,3 +292,24 @@ def test_transpose_device_layout_helper(rows, cols):
                                         C.c_void_p(torch.cuda.current_stream().cuda_stream)))
     torch.cuda.synchronize()
     assert torch.equal(dst, src.t().contiguous())
+
+
+@pytest.mark.parametrize("nx", [180, 208, 130])
+def test_sixteen_band_table_driven_instance(nx):
+    """104 < nx <= 208 with uniform table-building parameters: the 16-band instance of the table-driven kernel
+    (8 warps per CTA).  Forcing, B and the initial branch vary per member; fields of every 6th member."""
+    nmem = 40
+    st = ebm.SpaceTime(nx, 2000, 2)
+    forcings = [ebm.Forcing(-8.0 + 16.0 * m / (nmem - 1)) for m in range(nmem)]
+    pars = [_par(B=2.0 + 0.05 * (m % 4)) for m in range(nmem)]
+    inits = [warm_init(nx) if m % 2 == 0 else cold_init(nx) for m in range(nmem)]
+    o = oracle_classic(st, forcings, pars, inits, raw=True, seasonal=True)
+    r = ebm.integrate_ensemble("Classic", st, forcings, pars, inits, field_stride=6)
+    assert r.flags.max() == 0
+    tol = 1e-8                                     # finer grids: see test_ensemble_diag_fields_and_state
+    assert_close(r.final["E"], o["E"], tol, "final E")
+    assert_close(r.final["Tg"], o["Tg"], tol, "final Tg")
+    sel = np.arange(0, nmem, 6)
+    assert_close(r.raw, o["raw"][sel], tol, "raw")
+    assert_close(r.seasonal, o["seasonal"][sel], tol, "seasonal")
+    assert_close(r.diag[..., :2], oracle_diag_classic(o["seasonal"], st.x)[..., :2], tol, "diag")
