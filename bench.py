@@ -324,6 +324,7 @@ def main():
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms_total, k_ms = tt.tolist()
     bad = int(d_flags.max().item())
+    nbad = int((d_flags != 0).sum().item())
     ms_per_step = ms_total / args.steps
     value = total * years / (ms_per_step * 1e-3)
 
@@ -366,7 +367,7 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args.workload, nmem, years, world),
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-            "nan_flags": bad,
+            "nan_flags": bad, "nan_members_rank0": nbad,
         }
         print(json.dumps(line))
     if world > 1:
