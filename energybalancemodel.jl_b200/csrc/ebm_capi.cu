@@ -257,7 +257,9 @@ extern "C" int32_t ebm_classic_run_device(const ebm_grid_t* grid, const ebm_clas
   a.par = args->par; a.forc = args->forc; a.E = args->E; a.Tg = args->Tg;
   a.diag = args->diag; a.seasonal = args->seasonal; a.raw = args->raw; a.flags = args->flags;
   a.orig = (const long long*)args->member_index;
+  a.dbg = getenv("EBM_DBG") ? atoi(getenv("EBM_DBG")) : 0;
   const int ypl = opt.years_per_launch > 0 ? opt.years_per_launch : grid->dur;
+  static const int variant = getenv("EBM_CLASSIC_VARIANT") ? atoi(getenv("EBM_CLASSIC_VARIANT")) : 0;
   for (int y0 = 0; y0 < grid->dur; y0 += ypl) {
     a.year0 = y0;
     a.nyears = (y0 + ypl <= grid->dur) ? ypl : grid->dur - y0;
@@ -265,13 +267,17 @@ extern "C" int32_t ebm_classic_run_device(const ebm_grid_t* grid, const ebm_clas
       EBM_TRY(ebm_launch_classic_strict(a, stream));
     } else {
       // parameter-uniform 32-member groups take the table-driven kernel, everything else the general one
-      static const int variant = getenv("EBM_CLASSIC_VARIANT") ? atoi(getenv("EBM_CLASSIC_VARIANT")) : 0;
       // nx <= 104: the table-driven kernel takes the 32-member groups whose table-building parameters agree, its
       // per-member-coefficient instance the others; larger grids (or EBM_CLASSIC_VARIANT < 0): the band kernel
       a.uniform_split = (a.nx <= ebm_classic_uniform_max_nx() && variant >= 0) ? 1 : 0;
-      if (a.uniform_split) {
+      if (a.uniform_split && (variant == 0 || variant >= 20)) {
+        // round-2 kernel (classic_fused.cu): one CTA barrier per step
+        EBM_TRY(ebm_launch_classic_fused(a, variant, stream));
+        EBM_TRY(ebm_launch_classic_fused_general(a, stream));
+      } else if (a.uniform_split) {
+        // round-1 kernel (classic_uniform.cu), kept selectable for comparison: EBM_CLASSIC_VARIANT = 1..11
         EBM_TRY(ebm_launch_classic_uniform(a, variant, stream));
-        if (variant == 11) EBM_TRY(ebm_launch_classic_bands(a, stream));   // previous split, kept for comparison
+        if (variant == 11) EBM_TRY(ebm_launch_classic_bands(a, stream));
         else EBM_TRY(ebm_launch_classic_general(a, stream));
       } else {
         EBM_TRY(ebm_launch_classic_bands(a, stream));

@@ -51,6 +51,7 @@ struct ClassicKArgs {
   double* E; double* Tg;         // [nx][nmem]
   double* diag; double* seasonal; double* raw; int* flags;
   const long long* orig;         // NULL or [nmem]: original member index of slot m (output rows, field selection)
+  int dbg;                       // development switches (env EBM_DBG)
 };
 
 struct MizKArgs {
@@ -74,6 +75,8 @@ struct MizKArgs {
 int ebm_launch_classic_bands(const ClassicKArgs& a, cudaStream_t stream);
 int ebm_launch_classic_uniform(const ClassicKArgs& a, int variant, cudaStream_t stream);
 int ebm_launch_classic_general(const ClassicKArgs& a, cudaStream_t stream);
+int ebm_launch_classic_fused(const ClassicKArgs& a, int variant, cudaStream_t stream);          // classic_fused.cu
+int ebm_launch_classic_fused_general(const ClassicKArgs& a, cudaStream_t stream);
 int ebm_classic_uniform_max_nx();
 int ebm_launch_classic_strict(const ClassicKArgs& a, cudaStream_t stream);
 int ebm_launch_classic_single_step(const EbmGridTables& g, const double* par15, int ti, double f,
