@@ -81,7 +81,7 @@ struct Fused {
   double S0m, S2m, a0m, a2m, fac, fac2, one_dttau;   // TAB = false only
   long long thr_bits;                                  // bits of kLf / M (sign of M - kLf/E for E > 0)
   // identity
-  int tid, h, mi, pair, j0;
+  int tid, h, mi, pair, j0, nv;   // nv: real cells of this band (K unless the band holds pad cells)
   bool active, sel, cta_fields, pairsum;
   long long mo, msel;
   // state
@@ -140,6 +140,209 @@ struct Fused {
       }
     }
     if (ti == nt && cta_fields) { row(4, i) = 0.0; row(5, i) = 0.0; }
+  }
+
+  // Pad cells (a band's cells beyond nx) follow the band: frozen when every real cell of the band is ice, warm when
+  // every real cell is open water, untouched otherwise.  Called at launch and from the (rare) G path.
+  __device__ __forceinline__ void set_pads() {
+    if (nv < K && nv > 0) {
+      int hand = -1, hor = 0;
+#pragma unroll
+      for (int i = 0; i < K; ++i) if (i < nv) { hand &= __double2hiint(E[i]); hor |= __double2hiint(E[i]); }
+      const bool allice = hand < 0, allwater = hor >= 0;
+#pragma unroll
+      for (int i = 0; i < K; ++i) {
+        if (i >= nv) {
+          if (allice && !is_neg(E[i])) { E[i] = -10.0; Tg[i] = -10.0; rvalid = false; }
+          if (allwater && is_neg(E[i])) { E[i] = 100.0; Tg[i] = 10.0; rvalid = false; }
+        }
+      }
+    }
+  }
+
+  // ptxas keeps the instruction order of the source to a large extent (and a warp issues in order): code written
+  // cell after cell runs the cells' dependent chains one after the other (measured: 3 issue cycles per FP64
+  // instruction).  The hot paths below are therefore written statement-major over groups of GI cells -- every
+  // statement for all cells of the group before the next statement -- which gives each warp GI independent chains.
+  static constexpr int GI = 4;
+
+  // band-local elimination of the rows phase 1 left behind (diagonal in row 2, right-hand side in Tg): pivots in
+  // determinant form, P_i = w_0 ... w_i = d_i P_{i-1} - a_i^2 P_{i-2} (one dependent DFMA per row), so that the K
+  // reciprocals 1/w_i = P_{i-1}/P_i are independent of each other; then x_i + q_i x_{i+1} + s_i xL = y_i
+  __device__ __forceinline__ void eliminate(double& i_sl, double& i_ql, double& i_yl) {
+    double P[K + 1];
+    P[0] = 1.0;
+    {
+      double dg[K], ac[K];
+#pragma unroll
+      for (int i = 0; i < K; ++i) { dg[i] = row(2, i); ac[i] = (i == 0) ? 0.0 : coef(j0 + i).ac; }
+      P[1] = dg[0];
+#pragma unroll
+      for (int i = 1; i < K; ++i) P[i + 1] = fma(dg[i], P[i], -(ac[i] * P[i - 1]));
+    }
+    // 1 / w_i = P_{i-1} / P_i, GI rows at a time
+#pragma unroll
+    for (int i0 = 0; i0 < K; i0 += GI) {
+      double x[GI], e[GI];
+#pragma unroll
+      for (int g = 0; g < GI; ++g) if (i0 + g < K) asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x[g]) : "d"(P[i0 + g + 1]));
+#pragma unroll
+      for (int g = 0; g < GI; ++g) if (i0 + g < K) e[g] = fma(-P[i0 + g + 1], x[g], 1.0);
+#pragma unroll
+      for (int g = 0; g < GI; ++g) if (i0 + g < K) e[g] = fma(e[g], e[g], e[g]);
+#pragma unroll
+      for (int g = 0; g < GI; ++g) if (i0 + g < K) x[g] = fma(x[g], e[g], x[g]);
+#pragma unroll
+      for (int g = 0; g < GI; ++g) if (i0 + g < K) P[i0 + g] = P[i0 + g] * x[g];      // P[i] now holds 1 / w_i
+    }
+    // forward substitution: y and the left spike s are two chains of one dependent operation per row
+    double yprev = 0.0, sprev = 0.0;
+    double aj = sub(j0);
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+      const double cj = sub(j0 + i + 1);
+      const double iw = P[i];
+      const double tq = aj * iw;
+      const double ri = Tg[i] * iw;
+      const double y = (i == 0) ? ri : fma(-tq, yprev, ri);
+      const double s = (i == 0) ? tq : -tq * sprev;
+      const double q = cj * iw;
+      row(2, i) = q; row(3, i) = s; Tg[i] = y;
+      yprev = y; sprev = s; aj = cj;
+      if (i == K - 1) { i_sl = s; i_ql = q; i_yl = y; }
+    }
+  }
+
+  // physics of GI cells and their rows of the implicit system (classic.jl:47-62), statement-major.  MIXED = false:
+  // every cell of the band is ice (alpha = ai); the remaining masks -- frozen surface (C < 0, hence T0 < 0) and
+  // E' < 0 -- are bit masks on operands, exact in every case:
+  //   T = T0 [C<0];  mk = (T0<0) & (E'<0);  um = mk ? dt_tau/(M - kLf/E') : 0
+  //   diag = kappa_jj - cg_tau um;  rhs = Tg + dt_tau/cw E' [E'>=0] + um (ai S' - A + f)
+  // MIXED = true: cells of either sign (ice edge inside the band, E == 0): alpha, T and E' are selected per cell
+  // between the ice expressions above and the open-water ones of the W path; for an all-ice band the results are
+  // bit-identical to MIXED = false.
+  template <int I0, bool MIXED, bool SLOW, bool SUMNOW>
+  __device__ __forceinline__ void cell_group(const ClassicKArgs& a, const double fmA, const double S1c0, const double S1c1,
+                                             const double wold, const int season, const int ti, const int year,
+                                             double& dgT, double& dgE, double& dgA, double& dgX) {
+    constexpr int N = (I0 + GI <= K) ? GI : K - I0;
+    PhysA p[N]; double kjj[N], wj[N], rv[N], se[N], aw[N];
+#pragma unroll
+    for (int g = 0; g < N; ++g) {
+      p[g] = physA(j0 + I0 + g); kjj[g] = coef(j0 + I0 + g).kjj; rv[g] = row(0, I0 + g);
+      if constexpr (MIXED) { const PhysB q = physB(j0 + I0 + g); wj[g] = q.wts; aw[g] = q.aw; }
+      else wj[g] = pb[j0 + I0 + g].wts;
+      se[g] = (SUMNOW || SLOW) ? row(1, I0 + g) : 0.0;
+    }
+    double S[N], C[N], T[N], En[N], r[N], um[N], G[N];
+    int ice[N], tneg[N];   // 0 / -1: cell is ice; T0 < 0
+#pragma unroll
+    for (int g = 0; g < N; ++g) S[g] = fma(-S1c0, p[g].x, p[g].S0x);
+#pragma unroll
+    for (int g = 0; g < N; ++g) C[g] = fma(cg_tau, Tg[I0 + g], fmA);
+    if constexpr (MIXED) {
+#pragma unroll
+      for (int g = 0; g < N; ++g) {
+        ice[g] = __double2hiint(E[I0 + g]) >> 31;
+        const double al = ice[g] ? ai : (is_zero(E[I0 + g]) ? 0.0 : aw[g]);   // alpha = aw [E>0] + ai [E<0]       :47
+        C[g] = fma(al, S[g], C[g]);                                                                //                 :48
+      }
+    } else {
+#pragma unroll
+      for (int g = 0; g < N; ++g) C[g] = fma(ai, S[g], C[g]);                                  //                 :48
+    }
+#pragma unroll
+    for (int g = 0; g < N; ++g) G[g] = fma(-S1c1, p[g].x, p[g].S0x);
+#pragma unroll
+    for (int g = 0; g < N; ++g) T[g] = C[g] * rv[g];                // C / (M - kLf/E), reciprocal carried        :50
+#pragma unroll
+    for (int g = 0; g < N; ++g) G[g] = fma(ai, G[g], fmA);          // ai S[j,i+1] - A + f                         :61
+#pragma unroll
+    for (int g = 0; g < N; ++g) T[g] = and_mask(T[g], __double2hiint(C[g]) >> 31);   // T0 [T0 < 0], ice cells     :51
+#pragma unroll
+    for (int g = 0; g < N; ++g) En[g] = fma(-M, T[g], C[g]);
+#pragma unroll
+    for (int g = 0; g < N; ++g) En[g] = En[g] + Fb;
+#pragma unroll
+    for (int g = 0; g < N; ++g) En[g] = fma(dt, En[g], E[I0 + g]);                           //                 :53
+    if constexpr (MIXED) {
+#pragma unroll
+      for (int g = 0; g < N; ++g) {
+        const double Eo = E[I0 + g];
+        const bool water = is_pos(Eo) || (!ice[g] && !is_zero(Eo));   // E > 0 (denormals included)
+        const double Enw = fma(dt, C[g] + Fb, c1 * Eo);               // open water: the W path's expression
+        const bool cneg = __double2hiint(C[g]) < 0;
+        // sign of T0 = C / (M - kLf/E) of a water cell (matters when it freezes in this step): E > 0
+        const bool small = __double_as_longlong(Eo) < thr_bits;
+        tneg[g] = ice[g] ? (__double2hiint(C[g]) >> 31) : ((water && (cneg != small)) ? -1 : 0);
+        En[g] = water ? Enw : En[g];
+        T[g] = water ? Eo * inv_cw : (ice[g] ? T[g] : 0.0);           // T = E/cw [E>=0] + T0 [E<0][T0<0]            :51
+      }
+    }
+#pragma unroll
+    for (int g = 0; g < N; ++g) {
+      if constexpr (MIXED) {   // hemispheric mean of T: ice cells through accT, water cells through accEw (as in the W path)
+        accT = fma(wj[g], ice[g] ? T[g] : 0.0, accT);
+        accEw = fma(wj[g], ice[g] ? 0.0 : E[I0 + g], accEw);
+      } else {
+        accT = fma(wj[g], T[g], accT);
+      }
+    }
+#pragma unroll
+    for (int g = 0; g < N; ++g) r[g] = fma(M, En[g], -kLf);
+    {
+      double x[N], e[N];
+#pragma unroll
+      for (int g = 0; g < N; ++g) asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x[g]) : "d"(r[g]));
+#pragma unroll
+      for (int g = 0; g < N; ++g) e[g] = fma(-r[g], x[g], 1.0);
+#pragma unroll
+      for (int g = 0; g < N; ++g) e[g] = fma(e[g], e[g], e[g]);
+#pragma unroll
+      for (int g = 0; g < N; ++g) x[g] = fma(x[g], e[g], x[g]);
+#pragma unroll
+      for (int g = 0; g < N; ++g) r[g] = En[g] * x[g];              // 1/(M - kLf/E) of the new enthalpy
+    }
+#pragma unroll
+    for (int g = 0; g < N; ++g) um[g] = dt_tau * r[g];
+#pragma unroll
+    for (int g = 0; g < N; ++g) {
+      const int t0n = MIXED ? tneg[g] : (__double2hiint(C[g]) >> 31);
+      const int mk = t0n & (__double2hiint(En[g]) >> 31);                    // (T0<0) & (E<0), E updated        :56,61
+      um[g] = and_mask(um[g], mk);
+    }
+#pragma unroll
+    for (int g = 0; g < N; ++g) {
+      const double Ep = and_mask(En[g], ~(__double2hiint(En[g]) >> 31));     // E [E >= 0]                         :59
+      S[g] = fma(dttau_cw, Ep, Tg[I0 + g]);
+    }
+#pragma unroll
+    for (int g = 0; g < N; ++g) kjj[g] = fma(-cg_tau, um[g], kjj[g]);         // kappa_jj - dc/(M - kLf/E) [masked]   :56
+#pragma unroll
+    for (int g = 0; g < N; ++g) Tg[I0 + g] = fma(um[g], G[g], S[g]);          // right-hand side                  :58-62
+#pragma unroll
+    for (int g = 0; g < N; ++g) {
+      if (SUMNOW) se[g] += fma(wold, E[I0 + g], En[g]);
+      if (SLOW) {
+        sample(a, I0 + g, wj[g], p[g].x, En[g], T[g], se[g], season, ti, year, dgT, dgE, dgA, dgX);
+        if (ti == a.nt) se[g] = 0.0;
+      }
+      E[I0 + g] = En[g];
+    }
+#pragma unroll
+    for (int g = 0; g < N; ++g) {
+      row(0, I0 + g) = r[g]; row(2, I0 + g) = kjj[g];
+      if (SUMNOW || SLOW) row(1, I0 + g) = se[g];
+    }
+  }
+  template <int I0, bool MIXED, bool SLOW, bool SUMNOW>
+  __device__ __forceinline__ void cell_groups(const ClassicKArgs& a, const double fmA, const double S1c0, const double S1c1,
+                                              const double wold, const int season, const int ti, const int year,
+                                              double& dgT, double& dgE, double& dgA, double& dgX) {
+    if constexpr (I0 < K) {
+      cell_group<I0, MIXED, SLOW, SUMNOW>(a, fmA, S1c0, S1c1, wold, season, ti, year, dgT, dgE, dgA, dgX);
+      cell_groups<I0 + GI, MIXED, SLOW, SUMNOW>(a, fmA, S1c0, S1c1, wold, season, ti, year, dgT, dgE, dgA, dgX);
+    }
   }
 
   // ---- phases A + B of a step: physics, band-local elimination, reduction, post the interface rows.
@@ -213,135 +416,24 @@ struct Fused {
         const ElimB l = eb[j0 + K - 1], z = eb[j0];
         i_sl = l.be; i_ql = l.ga; i_yl = Tg[K - 1]; i_al = al; i_be = z.be; i_ga = z.ga;
       }
-    } else if (hand < 0 && !(a.dbg & 2)) {
-      // ---- I: every cell ice (alpha = ai).  The remaining masks of classic.jl:51,56-61 -- frozen surface (C < 0,
-      // hence T0 < 0) and E' < 0 -- are applied as bit masks on operands, exact in every case:
-      //   T = C<0 ? T0 : 0;  masked = (C<0) & (E'<0);  um = masked ? dt_tau/(M - kLf/E') : 0
-      //   diag = kappa_jj - cg_tau um;  rhs = Tg + dt_tau/cw max(E', 0) + um (ai S' - A + f)
-      done = true; gen = true;
+    }
+    if (!done) {
+      // ---- I / G: physics with the literal masks, then the band's elimination
+      gen = true;
+      const bool allice = hand < 0;
+      if (!allice) set_pads();
       if (!rvalid) {   // first step after open-water steps: r is a pure function of E
 #pragma unroll
         for (int i = 0; i < K; ++i) row(0, i) = E[i] * rcp3(fma(M, E[i], -kLf));
         rvalid = true;
       }
-      double Pm1 = 1.0, Pm2 = 1.0, yprev = 0.0, sprev = 0.0;
-      double aj = sub(j0);
-      // software pipeline: the loads of cell i+1 (tables, carried reciprocal, annual sum) are issued before the stores
-      // of cell i -- the scheduler cannot prove that table loads and row stores do not alias, and would otherwise
-      // run the cells strictly one after the other
-      PhysA p_n = physA(j0); CoefT c_n = coef(j0);
-      double cj_n = sub(j0 + 1), wj_n = pb[j0].wts, rv_n = row(0, 0), se_n = (SUMNOW || SLOW) ? row(1, 0) : 0.0;
-#pragma unroll
-      for (int i = 0; i < K; ++i) {
-        const int j = j0 + i;
-        const PhysA p = p_n; const CoefT c = c_n;
-        const double cj = cj_n, wj = wj_n, rv = rv_n;
-        double se = se_n;
-        if (i + 1 < K) {
-          p_n = physA(j + 1); c_n = coef(j + 1); cj_n = sub(j + 2); wj_n = pb[j + 1].wts; rv_n = row(0, i + 1);
-          if (SUMNOW || SLOW) se_n = row(1, i + 1);
-        }
-        const double Eo = E[i], Tgo = Tg[i];
-        const double S = fma(-S1c0, p.x, p.S0x);
-        const double C = fma(ai, S, fma(cg_tau, Tgo, fmA));        //                                              :48
-        const double T0 = C * rv;                                   // C / (M - kLf/E), reciprocal carried          :50
-        const double T = and_mask(T0, __double2hiint(C) >> 31);     // T0 [T0 < 0]                                   :51
-        const double En = fma(dt, fma(-M, T, C) + Fb, Eo);          //                                              :53
-        const int mk = (__double2hiint(C) & __double2hiint(En)) >> 31;   // (T0<0) & (E<0), E updated            :56,61
-        const double r = En * rcp3(fma(M, En, -kLf));               // 1/(M - kLf/E) of the new enthalpy
-        const double um = and_mask(dt_tau * r, mk);
-        const double Ep = and_mask(En, ~(__double2hiint(En) >> 31));   // E [E >= 0]                                 :59
-        const double G = fma(ai, fma(-S1c1, p.x, p.S0x), fmA);      // ai S[j,i+1] - A + f                          :61
-        const double rhs = fma(um, G, fma(dttau_cw, Ep, Tgo));      //                                           :58-62
-        const double diag = fma(-cg_tau, um, c.kjj);                // kappa_jj - dc/(M - kLf/E) [masked]            :56
-        // pivots in determinant form: P_i = w_0 ... w_i = d_i P_{i-1} - a_i^2 P_{i-2}; 1/w_i = P_{i-1}/P_i
-        const double P = (i == 0) ? diag : fma(diag, Pm1, -(c.ac * Pm2));
-        const double iw = Pm1 * rcp3(P);
-        const double tq = aj * iw;
-        const double y = (i == 0) ? rhs * iw : fma(-tq, yprev, rhs * iw);
-        const double s = (i == 0) ? tq : -tq * sprev;
-        const double q = cj * iw;
-        accT = fma(wj, T, accT);
-        row(0, i) = r;
-        if (SUMNOW || SLOW) {
-          if (SUMNOW) se += fma(wold, Eo, En);
-          if (SLOW) {
-            sample(a, i, wj, p.x, En, T, se, season, ti, year, dgT, dgE, dgA, dgX);
-            if (ti == nt) se = 0.0;
-          }
-          row(1, i) = se;
-        }
-        row(2, i) = q; row(3, i) = s;
-        E[i] = En; Tg[i] = y;
-        Pm2 = Pm1; Pm1 = P; yprev = y; sprev = s; aj = cj;
-        if (i == K - 1) { i_sl = s; i_ql = q; i_yl = y; }
-      }
-    }
-    if (!done) {
-      // ---- G: literal masks (classic.jl:47-63) as selects, fused with the elimination
-      gen = true;
-      if (!rvalid) {
-#pragma unroll
-        for (int i = 0; i < K; ++i) row(0, i) = E[i] * rcp3(fma(M, E[i], -kLf));
-        rvalid = true;
-      }
-      double Pm1 = 1.0, Pm2 = 1.0, yprev = 0.0, sprev = 0.0;
-      double aj = sub(j0);
-#pragma unroll
-      for (int i = 0; i < K; ++i) {
-        const int j = j0 + i;
-        const PhysA p = physA(j);
-        const PhysB pq = physB(j);
-        const CoefT c = coef(j);
-        const double cj = sub(j + 1);
-        const double S = fma(-S1c0, p.x, p.S0x);
-        const double Eo = E[i], Tgo = Tg[i];
-        const bool ice = is_neg(Eo), zero = is_zero(Eo);
-        const double alpha = ice ? ai : (zero ? 0.0 : pq.aw);       // alpha = aw [E>0] + ai [E<0]                  :47
-        const double inner = fma(cg_tau, Tgo, fmA);
-        const double C = fma(alpha, S, inner);                      //                                              :48
-        const double T0 = C * row(0, i);                            //                                              :50
-        const bool Cneg = is_neg(C);                                // E < 0: M - kLf/E > 0, so T0 < 0 <=> C < 0
-        const double Ti = Cneg ? T0 : 0.0;
-        const double T = ice ? Ti : Eo * inv_cw;                    //                                              :51
-        // same arithmetic as the W / I paths for water / ice cells
-        const double En_w = fma(dt, (C + Fb), c1 * Eo);
-        const double En_i = fma(dt, fma(-M, Ti, C) + Fb, Eo);
-        const double En = (ice | zero) ? En_i : En_w;               //                                              :53
-        const bool negn = is_neg(En);
-        // sign of T0 of a water cell (only matters when it freezes in this step): sign(C) * sign(M - kLf/E), E > 0
-        const bool small = __double_as_longlong(Eo) < thr_bits;
-        const bool T0neg = ice ? Cneg : ((!zero) & (Cneg != small));
-        const bool masked = T0neg & negn;                           // (T0<0) & (E<0), E updated                :56,61
-        const double r = En * rcp3(fma(M, En, -kLf));
-        row(0, i) = r;
-        const double u = dt_tau * r;
-        const double G = fma(ai, fma(-S1c1, p.x, p.S0x), fmA);
-        const double rhs = masked ? fma(u, G, Tgo) : (negn ? Tgo : fma(dttau_cw, En, Tgo));               // :58-62
-        const double diag = masked ? fma(-cg_tau, u, c.kjj) : c.kjj;                                       // :56
-        const double P = (i == 0) ? diag : fma(diag, Pm1, -(c.ac * Pm2));
-        const double iw = Pm1 * rcp3(P);
-        const double tq = aj * iw;
-        const double y = (i == 0) ? rhs * iw : fma(-tq, yprev, rhs * iw);
-        const double s = (i == 0) ? tq : -tq * sprev;
-        const double q = cj * iw;
-        row(2, i) = q; row(3, i) = s;
-        // hemispheric mean of T: ice cells through accT, water cells through accEw (as in the W path)
-        accT = fma(pq.wts, ice ? Ti : 0.0, accT);
-        accEw = fma(pq.wts, ice ? 0.0 : Eo, accEw);
-        if (SUMNOW || SLOW) {
-          double se = row(1, i);
-          if (SUMNOW) se += fma(wold, Eo, En);
-          if (SLOW) {
-            sample(a, i, pq.wts, p.x, En, T, se, season, ti, year, dgT, dgE, dgA, dgX);
-            if (ti == nt) se = 0.0;
-          }
-          row(1, i) = se;
-        }
-        E[i] = En; Tg[i] = y;
-        Pm2 = Pm1; Pm1 = P; yprev = y; sprev = s; aj = cj;
-        if (i == K - 1) { i_sl = s; i_ql = q; i_yl = y; }
-      }
+      // the all-ice specialisation only when no thread of the warp needs the general code (both give the same bits
+      // for an all-ice band, so the vote does not influence any result)
+      if (__all_sync(__activemask(), allice) && !(a.dbg & 2))
+        cell_groups<0, false, SLOW, SUMNOW>(a, fmA, S1c0, S1c1, wold, season, ti, year, dgT, dgE, dgA, dgX);
+      else
+        cell_groups<0, true, SLOW, SUMNOW>(a, fmA, S1c0, S1c1, wold, season, ti, year, dgT, dgE, dgA, dgX);
+      eliminate(i_sl, i_ql, i_yl);
     }
     if (gen) {
       double al = Tg[K - 2], be = row(3, K - 2), ga = row(2, K - 2);
@@ -497,8 +589,10 @@ __global__ void __maxnreg__(MAXR) classic_fused_kernel(const ClassicKArgs a) {
       const double lh = v ? a.g.lam_hi[j] : 0.0;
       PhysA p; PhysB q; CoefT c;
       if constexpr (TAB) {
-        // pad cells (j >= nx): decoupled rows that stay open water (S0x = 1000 keeps their E positive), weight 0
-        p.S0x = v ? fma(-pS2, x2, pS0) : 1000.0; q.aw = v ? fma(-pa2, x2, pa0) : 1.0;
+        // pad cells (j >= nx): decoupled rows of weight 0, bistable by construction -- as open water they absorb
+        // aw S = 1000 W/m^2 and stay warm, as ice ai S ~ 0 and they stay frozen -- so that they never change the path
+        // their band takes; Fused::advance flips them when the band's real cells have all changed sign
+        p.S0x = v ? fma(-pS2, x2, pS0) : 1e-3; q.aw = v ? fma(-pa2, x2, pa0) : 1e6;
         c.kjj = fma(fac, ll + lh, one_dttau); c.ac = (fac * ll) * (fac * ll);
       } else {   // geometry only: Fused::physA / physB / coef apply the member's parameters
         p.S0x = x2; q.aw = x2;
@@ -542,6 +636,7 @@ __global__ void __maxnreg__(MAXR) classic_fused_kernel(const ClassicKArgs a) {
   cx.inv_nt = 1.0 / nt; cx.inv_Lf = 1.0 / pLf;
   cx.thr_bits = __double_as_longlong(cx.kLf / cx.M);
   cx.tid = tid; cx.h = h; cx.mi = mi; cx.pair = pair; cx.j0 = band * K;
+  cx.nv = min(max(nx - band * K, 0), K);
   cx.active = active;
   cx.pairsum = (nt % 2) == 0;
   const long long mo = a.orig != nullptr ? a.orig[m] : m;   // ebm_classic_device_args_t.member_index
@@ -555,12 +650,14 @@ __global__ void __maxnreg__(MAXR) classic_fused_kernel(const ClassicKArgs a) {
   for (int i = 0; i < K; ++i) {
     const int j = cx.j0 + i;
     const bool v = j < nx;
-    cx.E[i] = (v ? a.E[(long long)j * nmem + m] : 1.0) + 0.0;     // pad cells: decoupled open-water rows; -0.0 -> +0.0
-    cx.Tg[i] = v ? a.Tg[(long long)j * nmem + m] : 0.0;
-    cx.row(0, i) = cx.E[i] * rcp3(fma(cx.M, cx.E[i], -cx.kLf));   // same expression as in the step: r is a pure function of E
+    cx.E[i] = (v ? a.E[(long long)j * nmem + m] : 100.0) + 0.0;   // -0.0 -> +0.0; pad cells: see set_pads
+    cx.Tg[i] = v ? a.Tg[(long long)j * nmem + m] : 10.0;
+    cx.row(0, i) = 0.0;
     cx.row(1, i) = 0.0;
     if (cx.cta_fields) { cx.row(4, i) = 0.0; cx.row(5, i) = 0.0; }
   }
+  cx.set_pads();
+  cx.rvalid = false;   // the first fused step computes the carried reciprocals from E
   // Forcing{true}: base == peak == cool, all breakpoints 0 -> the call is the constant `base`
   double fr[10];
 #pragma unroll
@@ -659,6 +756,8 @@ int ebm_launch_classic_fused(const ClassicKArgs& a, int variant, cudaStream_t st
     case 21: return launch_fused<13, 8, 168, true, true, true>(a, stream);    // dependent back substitution (fewer smem stores)
     case 22: return launch_fused<13, 8, 168, true, false, false>(a, stream);  // no band-pair rotation
     case 23: return launch_fused<13, 8, 255, true>(a, stream);                // 2 CTAs per SM, no register cap
+    case 24: if (a.nx <= 100) return launch_fused<10, 10, 136, true>(a, stream);   // 10 bands of 10 cells, 15 warps per SM
+             return launch_fused<13, 8, 168, true>(a, stream);
     default: return launch_fused<13, 8, 168, true>(a, stream);
   }
 }

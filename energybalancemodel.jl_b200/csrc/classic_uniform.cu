@@ -49,8 +49,9 @@ namespace {
 
 constexpr double kTwoPi = 6.283185307179586;
 
-// reciprocal for well-scaled operands: MUFU.RCP64H seed + two Newton steps (~1 ulp, no slow path)
+// reciprocal for well-scaled operands: MUFU.RCP64H seed + one cubic step (~1 ulp, no slow path)
 __device__ __forceinline__ double fast_rcp(double w) {
+#ifdef EBM_RCP_NEWTON2
   double x;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(w));
   double e = fma(-w, x, 1.0);
@@ -58,6 +59,14 @@ __device__ __forceinline__ double fast_rcp(double w) {
   e = fma(-w, x, 1.0);
   x = fma(x, e, x);
   return x;
+#else
+  // the seed is good to 2^-20 (measured, profiles/r2_microbench.txt): one cubic step reaches 1 ulp
+  double x;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(w));
+  const double e = fma(-w, x, 1.0);
+  const double t = fma(e, e, e);
+  return fma(x, t, x);
+#endif
 }
 // sign tests on the high word (integer pipe, not the FP64 pipe).  -0.0 counts as negative; the update
 // E + dt*(...) cannot produce it except by exact cancellation.
@@ -118,6 +127,7 @@ struct Ctx {
   // 16 members of 2 bands; thread-private [i][thread] (conflict free) when a warp holds all bands of 4 members
   __device__ __forceinline__ int cidx(int i) const { return WARPM ? (i * (WB * MW) + (int)threadIdx.x) : ((j0 + i) * MW + mi); }
   bool active, sel, cta_fields;
+  bool solver;   // this warp solves the CTA's interface systems (the warp that owns band pair 1: never the polar pair)
   long long m, mo, msel;   // slot in this launch, original member index (output rows), index among field-output members
   // state
   double E[K], Tg[K], accT;
@@ -373,12 +383,12 @@ struct Ctx {
     PHASE_MARK(1);   // elimination + reduction
     __syncthreads();
     PHASE_MARK(2);   // barrier 1 wait
-    // ---- interface system: WB unknowns per member.  Warp 0 solves it with two lanes per member working from
+    // ---- interface system: WB unknowns per member.  One warp solves it with two lanes per member working from
     // both ends towards the middle ("burn at both ends"), pivots carried as determinants D_k so that the
     // only dependent chain is one DFMA per row; all reciprocals are independent of each other.
-    if (tid < 2 * MW) {
+    if (solver) {
       constexpr int H = WB / 2;
-      const int half = tid / MW;                             // 0: rows 0..H-1 downwards, 1: rows WB-1..H upwards
+      const int half = (tid & 31) / MW;                      // 0: rows 0..H-1 downwards, 1: rows WB-1..H upwards
       double a_[H], d_[H], c_[H], r_[H];
 #pragma unroll
       for (int k = 0; k < H; ++k) {
@@ -472,7 +482,11 @@ __global__ void __maxnreg__(MAXR) classic_uniform_kernel(const ClassicKArgs a) {
   // warp = BPW bands x MW members (interface through shared memory and two CTA barriers), or, WARPM, warp = all WB
   // bands x 32/WB members (interface through shuffles, no barrier in the time loop)
   const int mi = WARPM ? (warp * (32 / WB) + (lane & (32 / WB - 1))) : (lane & (MW - 1));
-  const int band = WARPM ? (lane / (32 / WB)) : (warp * BPW + lane / MW);
+  // which band pair a warp owns rotates with the CTA index: in a partially ice-covered member only the polar bands
+  // take the expensive path, and without the rotation every resident CTA puts that warp on the same SM sub-partition
+  constexpr int NWARP = WB * MW / 32;
+  const int wrot = (a.dbg & 4) ? warp : (int)((warp + blockIdx.x) % NWARP);
+  const int band = WARPM ? (lane / (32 / WB)) : (wrot * BPW + lane / MW);
   const long long nmem = a.nmem;
   const long long m_first = (long long)blockIdx.x * MW;
   const long long m_raw = m_first + mi;
@@ -563,6 +577,7 @@ __global__ void __maxnreg__(MAXR) classic_uniform_kernel(const ClassicKArgs a) {
   cx.inv_cw = 1.0 / pcw; cx.dt = dt; cx.dt_tau = dt_tau; cx.dttau_cw = dt_tau * cx.inv_cw; cx.dc = dt_tau * cg_tau;
   cx.inv_nt = 1.0 / nt; cx.inv_Lf = 1.0 / pLf;
   cx.band = band; cx.mi = mi; cx.j0 = band * K;
+  cx.solver = WARPM ? false : ((a.dbg & 8) ? warp == 0 : (wrot == (NWARP > 1 ? 1 : 0)));
   cx.active = active;
   const long long mo = a.orig != nullptr ? a.orig[m] : m;   // ebm_classic_device_args_t.member_index
   cx.mo = mo;
