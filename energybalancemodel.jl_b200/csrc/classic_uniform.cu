@@ -176,6 +176,101 @@ struct Ctx {
     }
   }
 
+  static constexpr int GI = 4;
+  template <int I0, bool SLOW>
+  __device__ __forceinline__ void ice_group(const ClassicKArgs& a, const double fmA, const double S1c0, const double S1c1,
+                                            const int season, const int ti, const int year, bool& anymask,
+                                            double& dgT, double& dgE, double& dgA, double& dgX) {
+    constexpr int N = (I0 + GI <= K) ? GI : K - I0;
+    PhysTab p[N]; double rv[N], se[N];
+#pragma unroll
+    for (int g = 0; g < N; ++g) { p[g] = phys_at(j0 + I0 + g); rv[g] = rs.r(I0 + g); se[g] = sumE[cidx(I0 + g)]; }
+    double S[N], C[N], T[N], En[N], r[N], um[N], G[N];
+    int ice[N], tneg[N];   // 0 / -1
+#pragma unroll
+    for (int g = 0; g < N; ++g) S[g] = fma(-S1c0, p[g].S1x, p[g].S0x);                       // S[j,i]
+#pragma unroll
+    for (int g = 0; g < N; ++g) C[g] = fma(cg_tau, Tg[I0 + g], fmA);
+#pragma unroll
+    for (int g = 0; g < N; ++g) {
+      ice[g] = __double2hiint(E[I0 + g]) >> 31;
+      const double al = ice[g] ? ai : (is_zero(E[I0 + g]) ? 0.0 : p[g].aw);                 // alpha                  :47
+      C[g] = fma(al, S[g], C[g]);                                                           //                        :48
+    }
+#pragma unroll
+    for (int g = 0; g < N; ++g) G[g] = fma(-S1c1, p[g].S1x, p[g].S0x);                       // S[j,i+1]
+#pragma unroll
+    for (int g = 0; g < N; ++g) T[g] = C[g] * rv[g];                                          // T0 = C/(M - kLf/E)     :50
+#pragma unroll
+    for (int g = 0; g < N; ++g) G[g] = fma(ai, G[g], fmA);
+#pragma unroll
+    for (int g = 0; g < N; ++g) {
+      const int cneg = __double2hiint(C[g]) >> 31;              // for E < 0: M - kLf/E > 0, so T0 < 0 <=> C < 0
+      const double Eo = E[I0 + g];
+      // sign of T0 for a water cell (needed when it freezes in this step): sign(C) * sign(M - kLf/E), E > 0
+      const bool wneg = !is_zero(Eo) && ((cneg != 0) != is_neg(fma(M, Eo, -kLf))) && C[g] != 0.0;
+      tneg[g] = ice[g] ? cneg : (wneg ? -1 : 0);
+      const double Ti = __hiloint2double(__double2hiint(T[g]) & cneg, __double2loint(T[g]) & cneg);
+      T[g] = ice[g] ? Ti : Eo * inv_cw;                                                       //                        :51
+    }
+#pragma unroll
+    for (int g = 0; g < N; ++g) En[g] = fma(-M, T[g], C[g]);
+#pragma unroll
+    for (int g = 0; g < N; ++g) En[g] = En[g] + Fb;
+#pragma unroll
+    for (int g = 0; g < N; ++g) En[g] = fma(dt, En[g], E[I0 + g]);                           //                        :53
+#pragma unroll
+    for (int g = 0; g < N; ++g) r[g] = fma(M, En[g], -kLf);
+    {
+      double x[N], e[N];
+#pragma unroll
+      for (int g = 0; g < N; ++g) asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x[g]) : "d"(r[g]));
+#pragma unroll
+      for (int g = 0; g < N; ++g) e[g] = fma(-r[g], x[g], 1.0);
+#pragma unroll
+      for (int g = 0; g < N; ++g) e[g] = fma(e[g], e[g], e[g]);
+#pragma unroll
+      for (int g = 0; g < N; ++g) x[g] = fma(x[g], e[g], x[g]);
+#pragma unroll
+      for (int g = 0; g < N; ++g) r[g] = En[g] * x[g];                                        // 1/(M - kLf/E), E updated
+    }
+#pragma unroll
+    for (int g = 0; g < N; ++g) um[g] = dt_tau * r[g];
+#pragma unroll
+    for (int g = 0; g < N; ++g) {
+      const int mk = tneg[g] & (__double2hiint(En[g]) >> 31);                                 // (T0<0) & (E<0)      :56,61
+      anymask = anymask || (mk != 0);
+      um[g] = __hiloint2double(__double2hiint(um[g]) & mk, __double2loint(um[g]) & mk);
+    }
+#pragma unroll
+    for (int g = 0; g < N; ++g) {
+      const int pm = ~(__double2hiint(En[g]) >> 31);
+      const double Ep = __hiloint2double(__double2hiint(En[g]) & pm, __double2loint(En[g]) & pm);   // E [E >= 0]   :59
+      S[g] = fma(dttau_cw, Ep, Tg[I0 + g]);
+    }
+#pragma unroll
+    for (int g = 0; g < N; ++g) Tg[I0 + g] = fma(um[g], G[g], S[g]);                          // right-hand side     :58-62
+#pragma unroll
+    for (int g = 0; g < N; ++g) {
+      sample<SLOW>(a, I0 + g, p[g].wts, En[g], T[g], season, ti, year, se[g], dgT, dgE, dgA, dgX);
+      E[I0 + g] = En[g];
+    }
+#pragma unroll
+    for (int g = 0; g < N; ++g) {
+      rs.r(I0 + g) = r[g]; rs.q(I0 + g) = cg_tau * um[g];                                    // dc/(M - kLf/E) [masked] :56
+      sumE[cidx(I0 + g)] = se[g];
+    }
+  }
+  template <int I0, bool SLOW>
+  __device__ __forceinline__ void ice_groups(const ClassicKArgs& a, const double fmA, const double S1c0, const double S1c1,
+                                             const int season, const int ti, const int year, bool& anymask,
+                                             double& dgT, double& dgE, double& dgA, double& dgX) {
+    if constexpr (I0 < K) {
+      ice_group<I0, SLOW>(a, fmA, S1c0, S1c1, season, ti, year, anymask, dgT, dgE, dgA, dgX);
+      ice_groups<I0 + GI, SLOW>(a, fmA, S1c0, S1c1, season, ti, year, anymask, dgT, dgE, dgA, dgX);
+    }
+  }
+
   template <bool SLOW>
   __device__ __forceinline__ void step(const ClassicKArgs& a, const double f, const double S1c0, const double S1c1,
                                        const int ti, const int year) {
@@ -241,37 +336,11 @@ struct Ctx {
         }
       }
     } else {
-      double rv[K], se[K];                                  // carried reciprocals / annual sums: batched smem reads
-#pragma unroll
-      for (int i = 0; i < K; ++i) { rv[i] = rs.r(i); se[i] = sumE[cidx(i)]; }
-#pragma unroll
-      for (int i = 0; i < K; ++i) {
-        const PhysTab p = phys_at(j0 + i);
-        const double S = fma(-S1c0, p.S1x, p.S0x);
-        const double Eo = E[i], Tgo = Tg[i];
-        const bool ice = is_neg(Eo);
-        const double alpha = ice ? ai : (is_zero(Eo) ? 0.0 : p.aw);                               //     :47
-        const double C = fma(alpha, S, fma(cg_tau, Tgo, fmA));                                    //     :48
-        const double T0 = C * rv[i];                        // T0 = C/(M - kLf/E), 1/(M - kLf/E) carried     :50
-        const bool Cneg = C < 0.0;                          // for E < 0: M - kLf/E > 0, so T0 < 0 <=> C < 0
-        const double T = ice ? (Cneg ? T0 : 0.0) : Eo * inv_cw;                                   //     :51
-        const double En = fma(dt, fma(-M, T, C) + Fb, Eo);                                        //     :53
-        const bool negn = is_neg(En);
-        // sign of T0 for a water cell that freezes in this step: sign(C) * sign(M - kLf/E), E > 0
-        const bool T0neg = ice ? Cneg : (!is_zero(Eo) && (Cneg != is_neg(fma(M, Eo, -kLf))) && C != 0.0);
-        const bool masked = T0neg && negn;                  // (T0<0) & (E<0), E updated               :56,61
-        const double r = En * fast_rcp(fma(M, En, -kLf));   // 1/(M - kLf/E)
-        const double rhs_m = fma(dt_tau * r, fma(ai, fma(-S1c1, p.S1x, p.S0x), fmA), Tgo);        //     :58-62
-        const double rhs_w = fma(dttau_cw, En, Tgo);
-        rs.q(i) = masked ? dc * r : 0.0;                       // diag = kappa_jj - dc/(M - kLf/E)        :56
-        rs.r(i) = r;
-        anymask = anymask || masked;
-        E[i] = En;
-        Tg[i] = masked ? rhs_m : (negn ? Tgo : rhs_w);
-        sample<SLOW>(a, i, p.wts, En, T, season, ti, year, se[i], dgT, dgE, dgA, dgX);
-      }
-#pragma unroll
-      for (int i = 0; i < K; ++i) sumE[cidx(i)] = se[i];
+      // ptxas keeps the source order to a large extent and a warp issues in order: written cell after cell, the
+      // cells' dependent chains (C -> T0 -> E' -> reciprocal -> right-hand side, ~16 FP64 instructions deep) run one
+      // after the other.  Statement-major over groups of 4 cells gives the warp 4 independent chains; the masks of
+      // classic.jl:47-61 are bit masks / selects on operands, no branches.
+      ice_groups<0, SLOW>(a, fmA, S1c0, S1c1, season, ti, year, anymask, dgT, dgE, dgA, dgX);
     }
     if (SLOW && season == 2) dgT = accT * inv_nt;   // mean over the year of the hemispheric mean (linear)
     if (SLOW && ti == nt) accT = 0.0;
