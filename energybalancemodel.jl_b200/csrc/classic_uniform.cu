@@ -176,8 +176,8 @@ struct Ctx {
     }
   }
 
-  static constexpr int GI = 4;
-  template <int I0, bool SLOW>
+  static constexpr int GI = 3;
+  template <int I0, bool MIXED, bool SLOW>
   __device__ __forceinline__ void ice_group(const ClassicKArgs& a, const double fmA, const double S1c0, const double S1c1,
                                             const int season, const int ti, const int year, bool& anymask,
                                             double& dgT, double& dgE, double& dgA, double& dgX) {
@@ -193,9 +193,13 @@ struct Ctx {
     for (int g = 0; g < N; ++g) C[g] = fma(cg_tau, Tg[I0 + g], fmA);
 #pragma unroll
     for (int g = 0; g < N; ++g) {
-      ice[g] = __double2hiint(E[I0 + g]) >> 31;
-      const double al = ice[g] ? ai : (is_zero(E[I0 + g]) ? 0.0 : p[g].aw);                 // alpha                  :47
-      C[g] = fma(al, S[g], C[g]);                                                           //                        :48
+      if constexpr (MIXED) {
+        ice[g] = __double2hiint(E[I0 + g]) >> 31;
+        const double al = ice[g] ? ai : (is_zero(E[I0 + g]) ? 0.0 : p[g].aw);               // alpha                  :47
+        C[g] = fma(al, S[g], C[g]);                                                         //                        :48
+      } else {   // every cell of the band is ice (same bits as the general code)
+        C[g] = fma(ai, S[g], C[g]);
+      }
     }
 #pragma unroll
     for (int g = 0; g < N; ++g) G[g] = fma(-S1c1, p[g].S1x, p[g].S0x);                       // S[j,i+1]
@@ -206,12 +210,17 @@ struct Ctx {
 #pragma unroll
     for (int g = 0; g < N; ++g) {
       const int cneg = __double2hiint(C[g]) >> 31;              // for E < 0: M - kLf/E > 0, so T0 < 0 <=> C < 0
-      const double Eo = E[I0 + g];
-      // sign of T0 for a water cell (needed when it freezes in this step): sign(C) * sign(M - kLf/E), E > 0
-      const bool wneg = !is_zero(Eo) && ((cneg != 0) != is_neg(fma(M, Eo, -kLf))) && C[g] != 0.0;
-      tneg[g] = ice[g] ? cneg : (wneg ? -1 : 0);
       const double Ti = __hiloint2double(__double2hiint(T[g]) & cneg, __double2loint(T[g]) & cneg);
-      T[g] = ice[g] ? Ti : Eo * inv_cw;                                                       //                        :51
+      if constexpr (MIXED) {
+        const double Eo = E[I0 + g];
+        // sign of T0 for a water cell (needed when it freezes in this step): sign(C) * sign(M - kLf/E), E > 0
+        const bool wneg = !is_zero(Eo) && ((cneg != 0) != is_neg(fma(M, Eo, -kLf))) && C[g] != 0.0;
+        tneg[g] = ice[g] ? cneg : (wneg ? -1 : 0);
+        T[g] = ice[g] ? Ti : Eo * inv_cw;                                                     //                        :51
+      } else {
+        tneg[g] = cneg;
+        T[g] = Ti;
+      }
     }
 #pragma unroll
     for (int g = 0; g < N; ++g) En[g] = fma(-M, T[g], C[g]);
@@ -261,13 +270,13 @@ struct Ctx {
       sumE[cidx(I0 + g)] = se[g];
     }
   }
-  template <int I0, bool SLOW>
+  template <int I0, bool MIXED, bool SLOW>
   __device__ __forceinline__ void ice_groups(const ClassicKArgs& a, const double fmA, const double S1c0, const double S1c1,
                                              const int season, const int ti, const int year, bool& anymask,
                                              double& dgT, double& dgE, double& dgA, double& dgX) {
     if constexpr (I0 < K) {
-      ice_group<I0, SLOW>(a, fmA, S1c0, S1c1, season, ti, year, anymask, dgT, dgE, dgA, dgX);
-      ice_groups<I0 + GI, SLOW>(a, fmA, S1c0, S1c1, season, ti, year, anymask, dgT, dgE, dgA, dgX);
+      ice_group<I0, MIXED, SLOW>(a, fmA, S1c0, S1c1, season, ti, year, anymask, dgT, dgE, dgA, dgX);
+      ice_groups<I0 + GI, MIXED, SLOW>(a, fmA, S1c0, S1c1, season, ti, year, anymask, dgT, dgE, dgA, dgX);
     }
   }
 
@@ -340,7 +349,13 @@ struct Ctx {
       // cells' dependent chains (C -> T0 -> E' -> reciprocal -> right-hand side, ~16 FP64 instructions deep) run one
       // after the other.  Statement-major over groups of 4 cells gives the warp 4 independent chains; the masks of
       // classic.jl:47-61 are bit masks / selects on operands, no branches.
-      ice_groups<0, SLOW>(a, fmA, S1c0, S1c1, season, ti, year, anymask, dgT, dgE, dgA, dgX);
+      // all-ice specialisation (no alpha / T selects) when no thread of the warp needs the general code; both give
+      // the same bits for an all-ice band, so the vote does not influence any result
+      bool allice = true;
+#pragma unroll
+      for (int i = 0; i < K; ++i) allice = allice && is_neg(E[i]);
+      if (__all_sync(__activemask(), allice)) ice_groups<0, false, SLOW>(a, fmA, S1c0, S1c1, season, ti, year, anymask, dgT, dgE, dgA, dgX);
+      else ice_groups<0, true, SLOW>(a, fmA, S1c0, S1c1, season, ti, year, anymask, dgT, dgE, dgA, dgX);
     }
     if (SLOW && season == 2) dgT = accT * inv_nt;   // mean over the year of the hemispheric mean (linear)
     if (SLOW && ti == nt) accT = 0.0;
