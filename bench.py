@@ -13,6 +13,14 @@ classic EBM (nx=100, nt=2000), L0 diagnostics for every member-year.
   cpu_baseline : the C oracle (a port of the reference's algorithm, tridiagonal solve) with OpenMP on all
            host cores, on a bounded sample of the same workload.
 
+  kernel_ms_per_rank : CUDA-event time of the integrate call on every rank (min / max / all): load balance.
+  strong   : (N > 1) the fixed 65 536-member sweep dealt over the N ranks -- strong scaling beside the weak headline.
+  miz      : the C5 MIZ parameter sweep, 131 072 members x 5 years per GPU (N = 8: the full 16^5 grid), a few steps:
+           value, roofline, e2e, cpu_baseline, NaN census (value_finite_members counts finite members only).
+
+Every rank integrates the members `ebm.member_deal` hands it: 32-member packets dealt round-robin after a sort by
+initial regime (a contiguous cut gives one rank all the expensive members; round-1 VERDICT).
+
 `--impl reference` times that CPU implementation alone (rank 0 only).
 """
 from __future__ import annotations
@@ -48,6 +56,9 @@ def parse():
     ap.add_argument("--order", default="interleaved", choices=["branch", "interleaved"],
                     help="classic member order: SURVEY 8d's C4 definition (even members warm start, odd members cold start; "
                          "default) or branch-major (all warm starts, then all cold starts)")
+    ap.add_argument("--miz-members", type=int, default=131072, help="members per GPU of the MIZ sub-record")
+    ap.add_argument("--miz-years", type=int, default=5, help="simulated years of the MIZ sub-record")
+    ap.add_argument("--no-extra", action="store_true", help="skip the strong-scaling and MIZ sub-records")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()
@@ -57,15 +68,16 @@ def parse():
 ORDER = "interleaved"
 
 
-def classic_workload(ebm, nmem_total, offset, count, years):
-    """C4: H = nmem_total/2 forcings F = -20..+20, each run from a warm and from a cold start.  Member order
-    "interleaved" (SURVEY 8d, default): F_m = -20 + 40*(m//2)/(H-1), even m warm start, odd m cold start; "branch":
-    F_m = -20 + 40*(m mod H)/(H-1), first half warm, second half cold.  The library sorts members by regime itself."""
+def classic_workload(ebm, nmem_total, m, years):
+    """C4: H = nmem_total/2 forcings F = -20..+20, each run from a warm and from a cold start, for the global member
+    indices `m`.  Member order "interleaved" (SURVEY 8d, default): F_m = -20 + 40*(m//2)/(H-1), even m warm start, odd m
+    cold start; "branch": F_m = -20 + 40*(m mod H)/(H-1), first half warm, second half cold."""
     st = ebm.SpaceTime(100, 2000, years)
     p = ebm.default_parameters("Classic")
     prow = np.array([p[k] for k in ebm.CLASSIC_PAR_ORDER])
     H = max(nmem_total // 2, 1)
-    m = np.arange(offset, offset + count)
+    m = np.asarray(m, dtype=np.int64)
+    count = len(m)
     if ORDER == "interleaved":
         F = -20.0 + 40.0 * (m // 2) / max(H - 1, 1)
         warm = (m % 2) == 0
@@ -80,14 +92,22 @@ def classic_workload(ebm, nmem_total, offset, count, years):
     return st, par, forc, (E0, Tg0)
 
 
-def miz_workload(ebm, nmem_total, offset, count, years):
+def classic_cost_key(nmem_total):
+    """Regime of every member's initial state (0 warm / ice free, 2 cold / snowball): what the member costs."""
+    m = np.arange(nmem_total)
+    warm = (m % 2) == 0 if ORDER == "interleaved" else m < max(nmem_total // 2, 1)
+    return np.where(warm, 0, 2)
+
+
+def miz_workload(ebm, nmem_total, m, years):
     """C5: 16^5 tensor grid over (D, B, ai, k, m1) when nmem_total = 2^20 (row-major); zero init, F = 0."""
     st = ebm.SpaceTime(180, 2000, years, "sin")
     p = ebm.default_parameters("MIZ")
     order = list(ebm.MIZ_PAR_ORDER)
     prow = np.array([p[k] for k in order])
+    m = np.asarray(m, dtype=np.int64)
+    count = len(m)
     par = np.repeat(prow[None, :], count, axis=0)
-    m = np.arange(offset, offset + count)
     n = max(int(round(nmem_total ** 0.2)), 1)
     idx = [(m // n ** (4 - q)) % n for q in range(5)]
     lin = lambda lo, hi, i: lo + (hi - lo) * i / max(n - 1, 1)
@@ -139,6 +159,9 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- CPU arm
+PUBLISHED_MIZ_MY_PER_S = 0.256   # the reference's only figure: 60 000 MIZ steps in 1:57 (src/EnergyBalanceModel.jl:57-61)
+
+
 def host_threads():
     """All host cores this process may use (torchrun exports OMP_NUM_THREADS=1; the oracle sets its own count)."""
     try:
@@ -147,37 +170,64 @@ def host_threads():
         return max(1, os.cpu_count() or 1)
 
 
-def cpu_run(workload, nmem_total, years, sample_members, threads):
-    """Oracle (port of the reference algorithm) with OpenMP over members on a strided sample."""
+def cpu_run(workload, nmem_total, years, sample_members, threads, solver=0):
+    """Oracle (port of the reference algorithm) with OpenMP over members on a strided sample of the workload
+    (alternating even / odd members, so that both branches of C4 are sampled)."""
     import ebm_b200 as ebm
     import oracle
+    sample_members = max(1, min(sample_members, nmem_total))
     stride = max(nmem_total // sample_members, 1)
-    idx = np.arange(0, nmem_total, stride)[:sample_members]
+    k = np.arange(sample_members)
+    idx = np.minimum(k * stride + (k % 2), nmem_total - 1)
     if workload == "classic":
-        st, par, forc, (E0, Tg0) = classic_workload(ebm, nmem_total, 0, nmem_total, years)
+        st, par, forc, (E0, Tg0) = classic_workload(ebm, nmem_total, idx, years)
         t0 = time.perf_counter()
-        oracle.classic_run(st.x, st.t, years, st.winter.inx, st.summer.inx, par[idx], forc[idx], E0[idx], Tg0[idx],
-                           want_seasonal=True, nthreads=threads)
+        oracle.classic_run(st.x, st.t, years, st.winter.inx, st.summer.inx, par, forc, E0, Tg0,
+                           want_seasonal=True, nthreads=threads, solver=solver)
     else:
-        st, par, forc, init = miz_workload(ebm, nmem_total, 0, nmem_total, years)
+        st, par, forc, init = miz_workload(ebm, nmem_total, idx, years)
         t0 = time.perf_counter()
-        oracle.miz_run(st.x, st.t, years, st.winter.inx, st.summer.inx, st.grid_kind, par[idx], forc[idx],
-                       *[a[idx] for a in init], want_seasonal=True, nthreads=threads)
+        oracle.miz_run(st.x, st.t, years, st.winter.inx, st.summer.inx, st.grid_kind, par, forc,
+                       *init, want_seasonal=True, nthreads=threads)
     dt = time.perf_counter() - t0
-    return len(idx) * years / dt, dt, f"{len(idx)} members (stride {stride}) x {years} years, seasonal sampling on"
+    return len(idx) * years / dt, dt, f"{len(idx)} members (stride {stride}, even and odd alternating) x {years} years, seasonal sampling on"
+
+
+def cpu_baseline(workload, nmem_total, years, threads, sample_members=0, target_s=12.0):
+    """B-cpu of BASELINE.md 3: the oracle on all host cores, on a sample sized for >= ~10 s of CPU work (a short
+    probe fixes the rate first), plus -- classic only -- B-ref-proxy (dense LU of the nx x nx matrix every step, as
+    the reference's `\\` does, one thread) and B-pub (the reference's one published figure)."""
+    probe_members = max(2 * threads, 8)
+    yrs = years if workload == "classic" else min(years, 5)
+    if not sample_members:
+        v0, _, _ = cpu_run(workload, nmem_total, min(yrs, 2), probe_members, threads)
+        sample_members = int(max(probe_members, min(nmem_total, v0 * target_s / yrs)))
+        sample_members = max(threads, sample_members // threads * threads)
+    v, dt, desc = cpu_run(workload, nmem_total, yrs, sample_members, threads)
+    out = {"value": v, "unit": "member-years/s", "cores": threads, "kind": "port", "sample": desc, "seconds": dt,
+           "note": "C oracle restating src/classic.jl / src/miz.jl (tridiagonal solve / semi-smooth Newton, OpenMP over "
+                   "members); Julia is not installed, the reference itself cannot run",
+           "published_reference": {"value": PUBLISHED_MIZ_MY_PER_S, "unit": "member-years/s", "what": "MIZ, nx=180, nt=2000, "
+                                   "60 000 steps in 1:57 on the author's machine, 1 thread (src/EnergyBalanceModel.jl:57-61)"}}
+    if workload == "classic":
+        vp, dtp, descp = cpu_run("classic", nmem_total, 2, 4, 1, solver=1)
+        out["reference_proxy"] = {"value": vp, "unit": "member-years/s", "cores": 1, "seconds": dtp, "sample": descp,
+                                  "what": "same oracle with the dense LU of the nx x nx matrix every step, as "
+                                          "classic.jl:55-63 does, one thread (BASELINE.md B-ref-proxy)"}
+    return out
 
 
 def reference_arm(args, nmem, years):
-    import oracle
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = host_threads()
+    world = args.gpus
+    total = nmem * world
     sample = args.cpu_sample_members or (8 * threads if args.workload == "classic" else 2 * threads)
-    yrs = years
     vals = []
     for i in range(args.warmup + args.steps):
-        v, dt, desc = cpu_run(args.workload, nmem, yrs, sample, threads)
+        v, dt, desc = cpu_run(args.workload, total, years, sample, threads)
         if i >= args.warmup:
             vals.append((v, dt))
     value = sum(v * dt for v, dt in vals) / sum(dt for _, dt in vals)   # member-years / seconds over the K steps
@@ -200,6 +250,7 @@ def workload_config(workload, nmem, years, gpus):
     if workload == "classic":
         return {"workload": "C4 classic-EBM hysteresis ensemble: F=-20..+20 W/m^2, warm+cold start branches", "member_order": ORDER,
                 "members_per_gpu": nmem, "members_total": nmem * gpus, "years": years, "nx": 100, "nt": 2000,
+                "sharding": "32-member packets dealt round-robin over the ranks after a sort by initial regime (member_deal)",
                 "outputs": "L0 diagnostics (3 seasons x 4 scalars per member-year) + final state",
                 "l2": "flushed between timed iterations (256 MiB write); state is register-resident in any case"}
     return {"workload": "C5 MIZ parameter-sweep ensemble over (D,B,ai,k,m1), zero init, F=0",
@@ -209,6 +260,158 @@ def workload_config(workload, nmem, years, gpus):
 
 
 # ----------------------------------------------------------------------------- GPU arm
+class Env:
+    """torch / library handles shared by the passes of one bench process."""
+
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        import ebm_b200 as ebm
+        from ebm_b200 import _lib
+        self.torch, self.dist, self.ebm, self._lib = torch, dist, ebm, _lib
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.lib = _lib.load()
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)
+        self.stream = torch.cuda.current_stream()
+        self.peak_tf, self.peak_mhz = ebm.fp64_peak(self.local)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+
+def device_pass(env, workload, nmem_total, years, steps, warmup, sample_clocks=False):
+    """W warm-up + K timed steps of one workload; every rank integrates the members `member_deal` hands it.
+    Returns the measurements (max over ranks where it is a time) and what the e2e / CPU legs need."""
+    torch, dist, ebm, _lib, lib, dev = env.torch, env.dist, env.ebm, env._lib, env.lib, env.dev
+    world, rank = env.world, env.rank
+    key = classic_cost_key(nmem_total) if workload == "classic" else None
+    index = [ebm.member_deal(nmem_total, world, r, key=key) for r in range(world)]
+    mine = index[rank]
+    nmem = len(mine)
+    build = classic_workload if workload == "classic" else miz_workload
+    st, par, forc, init = build(ebm, nmem_total, mine, years)
+    nx, nt = st.nx, st.nt
+    grid = _lib.make_grid(st)
+    opt = _lib.make_options(device=env.local, lastonly=True, field_stride=0)
+    # device-resident inputs (member index fastest), allocated by torch.  member_deal hands over whole packets of
+    # one regime in regime order, which is the layout the classic kernels want (lanes of a warp = members of a regime)
+    f64 = torch.float64
+    d_par = torch.from_numpy(np.ascontiguousarray(par.T)).to(dev)
+    d_forc = torch.from_numpy(np.ascontiguousarray(forc.T)).to(dev)
+    d_init = [torch.from_numpy(np.ascontiguousarray(a.T)).to(dev) for a in init]
+    nstate = len(init) + (1 if workload == "miz" else 0)
+    d_state = [torch.empty((nx, nmem), dtype=f64, device=dev) for _ in range(nstate)]
+    d_diag = torch.full((nmem, years, 3, 4), float("nan"), dtype=f64, device=dev)
+    d_flags = torch.zeros(nmem, dtype=torch.int32, device=dev)
+    d_i64 = torch.zeros((2, nmem), dtype=torch.int64, device=dev)
+    stream = env.stream
+    if workload == "classic":
+        dargs = _lib.ClassicDeviceArgs(nmem, d_par.data_ptr(), d_forc.data_ptr(), d_state[0].data_ptr(),
+                                       d_state[1].data_ptr(), d_diag.data_ptr(), None, None, d_flags.data_ptr(), None)
+        run_dev = lambda: _lib.check(lib.ebm_classic_run_device(C.byref(grid), C.byref(dargs), C.byref(opt),
+                                                                C.c_void_p(stream.cuda_stream)))
+    else:
+        dargs = _lib.MizDeviceArgs(nmem, d_par.data_ptr(), d_forc.data_ptr(), *[t.data_ptr() for t in d_state],
+                                   d_diag.data_ptr(), None, None, d_i64[0].data_ptr(), d_i64[1].data_ptr(),
+                                   d_flags.data_ptr())
+        run_dev = lambda: _lib.check(lib.ebm_miz_run_device(C.byref(grid), C.byref(dargs), C.byref(opt),
+                                                            C.c_void_p(stream.cuda_stream)))
+    kern_ev = []
+
+    def step(timed):
+        env.flush.fill_(1)                                 # L2 flush
+        for k, a in enumerate(d_init):                     # restore the batch's initial state (device copy)
+            d_state[k].copy_(a)
+        if workload == "miz":
+            d_state[-1].zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        run_dev()
+        e1.record(stream)
+        if world > 1:                                      # NCCL over NVLink: gather the ensemble diagnostics to rank 0
+            ebm.gather_member_rows(d_diag, nmem_total, dst=0, index=index)
+        if timed:
+            kern_ev.append((e0, e1))
+
+    for _ in range(warmup):
+        step(False)
+    env.barrier()
+    sampler = ClockSampler(env.local) if (sample_clocks and rank == 0) else None
+    if sampler:
+        sampler.start()
+    launches0 = lib.ebm_launch_count()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record(stream)
+    for _ in range(steps):
+        step(True)
+    t1.record(stream)
+    env.barrier()
+    launches = lib.ebm_launch_count() - launches0
+    clocks = sampler.stop() if sampler else None
+    ms_total = t0.elapsed_time(t1)
+    k_ms = float(np.mean([a.elapsed_time(b) for a, b in kern_ev]))
+    k_all = [k_ms]
+    if world > 1:
+        tt = torch.tensor([ms_total], dtype=f64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_total = float(tt.item())
+        kk = [torch.zeros(1, dtype=f64, device=dev) for _ in range(world)]
+        dist.all_gather(kk, torch.tensor([k_ms], dtype=f64, device=dev))
+        k_all = [float(t.item()) for t in kk]
+    finite = torch.isfinite(d_state[0]).all(dim=0)         # members whose final state is finite
+    cnt = torch.tensor([int(finite.sum().item()), int((d_flags != 0).sum().item())], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(cnt)
+    ms_per_step = ms_total / steps
+    value = nmem_total * years / (ms_per_step * 1e-3)
+    flop_launch = FLOP_PER_CELL_STEP[workload] * nx * nt * float(years) * nmem
+    achieved = flop_launch / (max(k_all) * 1e-3) / 1e12
+    diag_bytes = d_diag.numel() * 8
+    res = {"value": value, "ms_per_step": ms_per_step, "steps": steps, "warmup": warmup, "launches": int(launches),
+           "clocks": clocks, "finite_members": int(cnt[0].item()), "flagged_members": int(cnt[1].item()),
+           "members_total": nmem_total, "members_this_rank": nmem, "years": years,
+           "kernel_ms_per_rank": {"min": min(k_all), "max": max(k_all), "all": k_all},
+           "achieved_tflops": achieved, "diag_bytes": diag_bytes, "max_kernel_ms": max(k_all),
+           "mean_T_last_year_member0": float(d_diag[0, -1, 2, 0].item()) if nmem else None}
+    res["_e2e_inputs"] = (st, par, forc, init, nmem)
+    return res
+
+
+def roofline_record(env, workload, res, traffic):
+    frac = res["achieved_tflops"] / env.peak_tf
+    kernel = ("classic_uniform_kernel<13,8,16,168> (parameter-uniform 32-member groups; its per-member-coefficient instance "
+              "takes the rest)" if workload == "classic" else "miz_fast_kernel<6>")
+    return {"bound": "fp64", "achieved": res["achieved_tflops"], "peak": env.peak_tf, "unit": "TFLOP/s", "frac": frac,
+            "traffic": traffic.get(workload, {}).get("bytes") if traffic else None,
+            "traffic_source": traffic.get(workload, {}).get("source") if traffic else None,
+            "peak_source": "measured in this run by ebm_fp64_peak (dependent-free DFMA chains); MEASURED_PEAKS.json has no FP64 entry",
+            "peak_nominal": NOMINAL_FP64_TFLOPS, "frac_of_nominal": res["achieved_tflops"] / NOMINAL_FP64_TFLOPS,
+            "kernel": kernel, "kernel_ms": res["max_kernel_ms"],
+            "algorithmic_flop_per_cell_step": FLOP_PER_CELL_STEP[workload],
+            "hbm_output_stream": {"bytes_per_launch": res["diag_bytes"],
+                                  "achieved_gbs": res["diag_bytes"] / (res["max_kernel_ms"] * 1e-3) / 1e9,
+                                  "peak_gbs": _measured_hbm()}}
+
+
+def _traffic():
+    """DRAM bytes of one launch of the default configurations, captured with ncu (profiles/r2_traffic.json)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r2_traffic.json")) as fh:
+            return json.load(fh)
+    except Exception:
+        return None
+
+
 def main():
     args = parse()
     global ORDER
@@ -218,160 +421,63 @@ def main():
     if args.impl == "reference":
         reference_arm(args, nmem, years)
         return
-
-    import torch
-    import torch.distributed as dist
-    import ebm_b200 as ebm
-    from ebm_b200 import _lib
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    lib = _lib.load()
-
+    env = Env()
+    world, rank = env.world, env.rank
     total = nmem * world
-    build = classic_workload if args.workload == "classic" else miz_workload
-    st, par, forc, init = build(ebm, total, rank * nmem, nmem, years)
-    nx, nt = st.nx, st.nt
-    grid = _lib.make_grid(st)
-    opt = _lib.make_options(device=local, lastonly=True, field_stride=0)
+    traffic = _traffic()
 
-    # ---- device-resident inputs (member index fastest), allocated by torch.  For the classic kernels (lane = member)
-    # the resident layout is sorted by the regime of the initial state, exactly what ebm_classic_run does internally
-    # for host buffers; member_index tells the library where each slot's output rows go (original member order).
-    f64 = torch.float64
-    slot_of = None
-    if args.workload == "classic":
-        ice = (init[0] < 0).sum(axis=1)
-        key = np.where(ice == 0, 0, np.where(ice == nx, 2, 1))
-        perm = np.argsort(key, kind="stable")
-        if not np.array_equal(perm, np.arange(nmem)):
-            slot_of = torch.from_numpy(perm.astype(np.int64)).to(dev)
-            par_d, forc_d, init_d = par[perm], forc[perm], [a[perm] for a in init]
-    if slot_of is None:
-        par_d, forc_d, init_d = par, forc, init
-    d_par = torch.from_numpy(np.ascontiguousarray(par_d.T)).to(dev)
-    d_forc = torch.from_numpy(np.ascontiguousarray(forc_d.T)).to(dev)
-    d_init = [torch.from_numpy(np.ascontiguousarray(a.T)).to(dev) for a in init_d]
-    nstate = len(init) + (1 if args.workload == "miz" else 0)
-    d_state = [torch.empty((nx, nmem), dtype=f64, device=dev) for _ in range(nstate)]
-    d_diag = torch.full((nmem, years, 3, 4), float("nan"), dtype=f64, device=dev)
-    d_flags = torch.zeros(nmem, dtype=torch.int32, device=dev)
-    d_i64 = torch.zeros((2, nmem), dtype=torch.int64, device=dev)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    stream = torch.cuda.current_stream()
-
-    if args.workload == "classic":
-        dargs = _lib.ClassicDeviceArgs(nmem, d_par.data_ptr(), d_forc.data_ptr(), d_state[0].data_ptr(),
-                                       d_state[1].data_ptr(), d_diag.data_ptr(), None, None, d_flags.data_ptr(),
-                                       slot_of.data_ptr() if slot_of is not None else None)
-        run_dev = lambda: _lib.check(lib.ebm_classic_run_device(C.byref(grid), C.byref(dargs), C.byref(opt),
-                                                                C.c_void_p(stream.cuda_stream)))
-    else:
-        dargs = _lib.MizDeviceArgs(nmem, d_par.data_ptr(), d_forc.data_ptr(), *[t.data_ptr() for t in d_state],
-                                   d_diag.data_ptr(), None, None, d_i64[0].data_ptr(), d_i64[1].data_ptr(),
-                                   d_flags.data_ptr())
-        run_dev = lambda: _lib.check(lib.ebm_miz_run_device(C.byref(grid), C.byref(dargs), C.byref(opt),
-                                                            C.c_void_p(stream.cuda_stream)))
-
-    kern_ms = []
-
-    def step(timed):
-        flush.fill_(1)                                     # L2 flush
-        for k, a in enumerate(d_init):                     # restore the batch's initial state (device copy)
-            d_state[k].copy_(a)
-        if args.workload == "miz":
-            d_state[-1].zero_()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        run_dev()
-        e1.record(stream)
-        if world > 1:                                      # NCCL over NVLink: gather the ensemble diagnostics to rank 0
-            ebm.gather_member_rows(d_diag, total, dst=0)
-        if timed:
-            kern_ms.append((e0, e1))
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(args.warmup):
-        step(False)
-    barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    launches0 = lib.ebm_launch_count()
-    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0.record(stream)
-    for _ in range(args.steps):
-        step(True)
-    t1.record(stream)
-    barrier()
-    launches = lib.ebm_launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
-    ms_total = t0.elapsed_time(t1)
-    k_ms = float(np.mean([a.elapsed_time(b) for a, b in kern_ms]))
-    if world > 1:
-        tt = torch.tensor([ms_total, k_ms], dtype=f64, device=dev)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms_total, k_ms = tt.tolist()
-    bad = int(d_flags.max().item())
-    nbad = int((d_flags != 0).sum().item())
-    ms_per_step = ms_total / args.steps
-    value = total * years / (ms_per_step * 1e-3)
-
-    # ---- roofline of the dominant kernel (this rank's launch)
-    flop_launch = FLOP_PER_CELL_STEP[args.workload] * nx * nt * float(years) * nmem
-    achieved = flop_launch / (k_ms * 1e-3) / 1e12
-    peak_tf, peak_mhz = ebm.fp64_peak(local)
-    diag_bytes = d_diag.numel() * 8
-    roof = {"bound": "fp64", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-            "traffic": None,
-            "traffic_note": "not captured for this launch; ncu --set full on the short profiling command (profiles/README.md): "
-                            "classic 29.7 MB read + 0.7 MB written, MIZ 73 MB + 26 MB per launch -- initial state in, "
-                            "diagnostics and final state out; the kernels are FP64-bound, not HBM-bound",
-            "peak_source": "measured in this run by ebm_fp64_peak (dependent-free DFMA chains); "
-                           "MEASURED_PEAKS.json has no FP64 entry",
-            "peak_nominal": NOMINAL_FP64_TFLOPS, "frac_of_nominal": achieved / NOMINAL_FP64_TFLOPS,
-            "kernel": "classic_uniform_kernel (parameter-uniform 32-member groups; classic_bands_kernel takes the rest)"
-                      if args.workload == "classic" else "miz_warp_kernel",
-            "kernel_ms": k_ms, "algorithmic_flop_per_cell_step": FLOP_PER_CELL_STEP[args.workload],
-            "hbm_output_stream": {"bytes_per_launch": diag_bytes, "achieved_gbs": diag_bytes / (k_ms * 1e-3) / 1e9,
-                                  "peak_gbs": _measured_hbm()}}
-
-    # ---- end to end through the host-buffer C ABI (pinned inputs, H2D + kernel + D2H timed)
+    # ---- headline: K timed steps of the requested workload, weak scaling (nmem members per GPU)
+    res = device_pass(env, args.workload, total, years, args.steps, args.warmup, sample_clocks=True)
+    roof = roofline_record(env, args.workload, res, traffic if (args.members == 0 and args.years == 0) else None)
     e2e = None
     if not args.no_e2e:
-        e2e = run_e2e(args, ebm, lib, _lib, st, par, forc, init, nmem, years, local, world, total)
-
+        e2e = run_e2e(env, args.workload, res["_e2e_inputs"], years, total)
     cpu = None
     if rank == 0 and not args.no_cpu:
-        import oracle
-        thr = host_threads()
-        sample = args.cpu_sample_members or (8 * thr if args.workload == "classic" else 2 * thr)
-        v, dt, desc = cpu_run(args.workload, total, years, sample, thr)
-        cpu = {"value": v, "unit": "member-years/s", "cores": thr, "kind": "port", "sample": desc, "seconds": dt}
+        cpu = cpu_baseline(args.workload, total, years, host_threads(), args.cpu_sample_members)
+
+    # ---- sub-records (default classic run only): strong scaling of the fixed 65 536-member sweep, and the MIZ sweep
+    strong = miz = None
+    if args.workload == "classic" and not args.no_extra:
+        if world == 1:
+            strong = {"members_total": total, "value": res["value"], "unit": "member-years/s",
+                      "note": "N = 1: the strong-scaling run is the headline run"}
+        else:
+            sres = device_pass(env, "classic", nmem, years, min(args.steps, 3), 1)
+            strong = {"members_total": nmem, "members_per_gpu": nmem // world, "years": years, "value": sres["value"],
+                      "unit": "member-years/s", "ms_per_step": sres["ms_per_step"], "steps": sres["steps"], "warmup": 1,
+                      "kernel_ms_per_rank": sres["kernel_ms_per_rank"],
+                      "note": "the fixed 65 536-member sweep (SURVEY 8e) dealt over the N ranks; NCCL gather inside the timed step"}
+        mz_members, mz_years = args.miz_members, args.miz_years
+        mres = device_pass(env, "miz", mz_members * world, mz_years, min(args.steps, 3), 1)
+        mroof = roofline_record(env, "miz", mres, traffic)
+        me2e = None if args.no_e2e else run_e2e(env, "miz", mres["_e2e_inputs"], mz_years, mz_members * world)
+        mcpu = cpu_baseline("miz", mz_members * world, mz_years, host_threads()) if (rank == 0 and not args.no_cpu) else None
+        fin = mres["finite_members"]
+        miz = {"metric": "member_years_per_sec", "value": mres["value"], "unit": "member-years/s",
+               "value_finite_members": mres["value"] * fin / max(mres["members_total"], 1),
+               "nan_members": mres["members_total"] - fin, "flagged_members": mres["flagged_members"],
+               "ms_per_step": mres["ms_per_step"], "steps": mres["steps"], "warmup": 1,
+               "config": workload_config("miz", mz_members, mz_years, world), "roofline": mroof,
+               "kernel_ms_per_rank": mres["kernel_ms_per_rank"], "e2e": me2e, "cpu_baseline": mcpu,
+               "gpu_launches": mres["launches"],
+               "note": "members whose state is non-finite at the end (the reference algorithm itself blows up for part of "
+                       "this sweep, DESIGN.md 2) are counted in `value` and excluded from `value_finite_members`"}
 
     if rank == 0:
         line = {
-            "metric": "member_years_per_sec", "value": value, "unit": "member-years/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "metric": "member_years_per_sec", "value": res["value"], "unit": "member-years/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args.workload, nmem, years, world),
-            "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-            "nan_flags": bad, "nan_members_rank0": nbad,
+            "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": res["launches"], "clocks": res["clocks"],
+            "kernel_ms_per_rank": res["kernel_ms_per_rank"],
+            "nan_members": res["members_total"] - res["finite_members"], "flagged_members": res["flagged_members"],
+            "strong": strong, "miz": miz,
         }
         print(json.dumps(line))
     if world > 1:
-        dist.destroy_process_group()
+        env.dist.destroy_process_group()
 
 
 def _measured_hbm():
@@ -382,20 +488,23 @@ def _measured_hbm():
         return 6650.0
 
 
-def run_e2e(args, ebm, lib, _lib, st, par, forc, init, nmem, years, local, world, total):
-    import torch
-    import torch.distributed as dist
+def run_e2e(env, workload, inputs, years, total):
+    """The same metric through the host-buffer C ABI: pinned host inputs -> H2D -> (regime sort) -> kernel -> D2H of the
+    diagnostics and the final state, all inside the timed region; one untimed call first (the library keeps its device
+    workspace between calls), then ONE timed call -- a step is seconds long, so one call is already a stable sample."""
+    torch, dist, _lib, lib = env.torch, env.dist, env._lib, env.lib
+    st, par, forc, init, nmem = inputs
     nx = st.nx
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
     h_par, h_forc = pin(par), pin(forc)
     h_init = [pin(a) for a in init]
     h_diag = torch.empty((nmem, years, 3, 4), dtype=torch.float64).pin_memory()
-    nfin = len(init) + (1 if args.workload == "miz" else 0)
+    nfin = len(init) + (1 if workload == "miz" else 0)
     h_fin = [torch.empty((nmem, nx), dtype=torch.float64).pin_memory() for _ in range(nfin)]
     grid = _lib.make_grid(st)
-    opt = _lib.make_options(device=local, lastonly=True, field_stride=0)
+    opt = _lib.make_options(device=env.local, lastonly=True, field_stride=0)
     P = lambda t: C.cast(t.data_ptr(), C.POINTER(C.c_double))
-    if args.workload == "classic":
+    if workload == "classic":
         out = _lib.ClassicOutputs(P(h_diag), None, None, P(h_fin[0]), P(h_fin[1]), None)
         call = lambda: _lib.check(lib.ebm_classic_run(C.byref(grid), nmem, P(h_par), P(h_forc), P(h_init[0]), P(h_init[1]),
                                                       C.byref(opt), C.byref(out)))
@@ -405,25 +514,19 @@ def run_e2e(args, ebm, lib, _lib, st, par, forc, init, nmem, years, local, world
                                                   C.byref(opt), C.byref(out)))
     h2d = sum(t.numel() * 8 for t in [h_par, h_forc] + h_init)
     d2h = h_diag.numel() * 8 + sum(t.numel() * 8 for t in h_fin)
-    # one untimed call first: the library keeps its device workspace between calls (a user integrating in a loop pays
-    # the cudaMalloc of the GB-sized staging buffers once), everything else -- H2D, reorder, kernel, D2H -- is timed
     call()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    n = 1
+    env.barrier()
     t0 = time.perf_counter()
-    for _ in range(n):
-        call()
+    call()
     torch.cuda.synchronize()
-    dt = (time.perf_counter() - t0) / n
-    if world > 1:
-        tt = torch.tensor([dt], dtype=torch.float64, device=torch.device("cuda", local))
+    dt = time.perf_counter() - t0
+    if env.world > 1:
+        tt = torch.tensor([dt], dtype=torch.float64, device=env.dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dt = float(tt.item())
     return {"value": total * years / dt, "unit": "member-years/s", "h2d_bytes_per_step": int(h2d),
-            "d2h_bytes_per_step": int(d2h), "seconds_per_step": dt, "steps": n,
-            "api": "ebm_classic_run (host-buffer C ABI)" if args.workload == "classic" else "ebm_miz_run (host-buffer C ABI)",
+            "d2h_bytes_per_step": int(d2h), "seconds_per_step": dt, "steps": 1, "untimed_calls_before": 1,
+            "api": "ebm_classic_run (host-buffer C ABI)" if workload == "classic" else "ebm_miz_run (host-buffer C ABI)",
             "result_check": {"mean_T_last_year_member0": float(h_diag[0, -1, 2, 0])}}
 
 

@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(MAXT, MINB) classic_bands_kernel(const Classic
   const int lane = tid & 31, warp = tid >> 5;
   const int mi = lane & (MW - 1);
   const int band_raw = warp * BPW + lane / MW;
-  const int band = band_raw < W ? band_raw : W - 1;   // threads of a partly filled last warp shadow the last band
+  const int band = band_raw < W ? band_raw : W - 1;   // (the launcher rounds W up to whole warps: band_raw < W always)
   const long long m_raw = (long long)blockIdx.x * MW + mi;
   const bool active = m_raw < a.nmem && band_raw < W;
   if (a.uniform_split && ebm_classic_group_uniform<MW>(a.par, a.nmem, (long long)blockIdx.x * MW, mi)) return;
@@ -329,7 +329,11 @@ __global__ void __launch_bounds__(MAXT, MINB) classic_bands_kernel(const Classic
 template <int K, int MW, int MAXT, int MINB>
 int launch_variant(const ClassicKArgs& a0, cudaStream_t stream) {
   ClassicKArgs a = a0;
+  // whole warps only: with MW = 16 an odd band count gets one more band of pad cells (decoupled rows), so that no
+  // thread has to shadow another thread's band (two threads updating the same shared-memory slots)
+  constexpr int BPW = 32 / MW;
   a.W = (a.nx + K - 1) / K;
+  a.W = (a.W + BPW - 1) / BPW * BPW;
   if (a.W < 1 || a.W * MW > MAXT) {
     ebm_set_error("classic_bands: nx=%d needs %d bands of %d cells (> %d threads)", a.nx, a.W, K, MAXT);
     return EBM_ERR_UNSUPPORTED;

@@ -758,7 +758,7 @@ int ebm_launch_classic_fused(const ClassicKArgs& a, int variant, cudaStream_t st
     case 23: return launch_fused<13, 8, 255, true>(a, stream);                // 2 CTAs per SM, no register cap
     case 24: if (a.nx <= 100) return launch_fused<10, 10, 136, true>(a, stream);   // 10 bands of 10 cells, 15 warps per SM
              return launch_fused<13, 8, 168, true>(a, stream);
-    default: return launch_fused<13, 8, 168, true>(a, stream);
+    default: return launch_fused<13, 8, 168, true>(a, stream);                // EBM_CLASSIC_VARIANT = 20
   }
 }
 

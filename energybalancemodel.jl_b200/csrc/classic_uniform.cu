@@ -68,8 +68,8 @@ __device__ __forceinline__ double fast_rcp(double w) {
   return fma(x, t, x);
 #endif
 }
-// sign tests on the high word (integer pipe, not the FP64 pipe).  -0.0 counts as negative; the update
-// E + dt*(...) cannot produce it except by exact cancellation.
+// sign tests on the high word (integer pipe, not the FP64 pipe).  The state never holds -0.0: it is normalised when
+// loaded, and E + dt*(...) cannot produce it (an exact cancellation rounds to +0.0).
 __device__ __forceinline__ bool is_neg(double v) { return __double2hiint(v) < 0; }
 __device__ __forceinline__ bool is_zero(double v) { return ((__double2hiint(v) << 1) | __double2loint(v)) == 0; }
 
@@ -674,7 +674,9 @@ __global__ void __maxnreg__(MAXR) classic_uniform_kernel(const ClassicKArgs a) {
   for (int i = 0; i < K; ++i) {
     const int j = cx.j0 + i;
     const bool v = j < nx;
-    cx.E[i] = v ? a.E[(long long)j * nmem + m] : 1.0;     // pad cells: decoupled open-water rows
+    // -0.0 -> +0.0: classic.jl:47's masks are E>0 / E<0 (alpha = 0 at either zero), the sign-bit tests below would
+    // take -0.0 for ice; an FMA result is -0.0 only if both addends are, so the state never produces one itself
+    cx.E[i] = (v ? a.E[(long long)j * nmem + m] : 1.0) + 0.0;     // pad cells: decoupled open-water rows
     cx.Tg[i] = v ? a.Tg[(long long)j * nmem + m] : 0.0;
     sumE[cx.cidx(i)] = 0.0;
     cx.rs.r(i) = cx.E[i] * fast_rcp(fma(cx.M, cx.E[i], -cx.kLf));   // same expression as in the step: r is a pure function of E

@@ -270,12 +270,13 @@ extern "C" int32_t ebm_classic_run_device(const ebm_grid_t* grid, const ebm_clas
       // nx <= 104: the table-driven kernel takes the 32-member groups whose table-building parameters agree, its
       // per-member-coefficient instance the others; larger grids (or EBM_CLASSIC_VARIANT < 0): the band kernel
       a.uniform_split = (a.nx <= ebm_classic_uniform_max_nx() && variant >= 0) ? 1 : 0;
-      if (a.uniform_split && (variant == 0 || variant >= 20)) {
-        // round-2 kernel (classic_fused.cu): one CTA barrier per step
+      if (a.uniform_split && variant >= 20) {
+        // experimental one-barrier kernel (classic_fused.cu; EBM_CLASSIC_VARIANT >= 20): measured slower than the
+        // two-barrier kernel in every regime, kept for the record
         EBM_TRY(ebm_launch_classic_fused(a, variant, stream));
         EBM_TRY(ebm_launch_classic_fused_general(a, stream));
       } else if (a.uniform_split) {
-        // round-1 kernel (classic_uniform.cu), kept selectable for comparison: EBM_CLASSIC_VARIANT = 1..11
+        // the production kernel (classic_uniform.cu); EBM_CLASSIC_VARIANT = 1..11 select its tuning instantiations
         EBM_TRY(ebm_launch_classic_uniform(a, variant, stream));
         if (variant == 11) EBM_TRY(ebm_launch_classic_bands(a, stream));
         else EBM_TRY(ebm_launch_classic_general(a, stream));

@@ -7,7 +7,7 @@ from ebm_b200 import _lib
 lib = _lib.load()
 nmem, years = 65536, int(sys.argv[1]) if len(sys.argv) > 1 else 1
 bench.ORDER = sys.argv[2] if len(sys.argv) > 2 else "interleaved"
-st, par, forc, (E0, Tg0) = bench.classic_workload(ebm, nmem, 0, nmem, years)
+st, par, forc, (E0, Tg0) = bench.classic_workload(ebm, nmem, np.arange(nmem), years)
 pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
 h = [pin(par), pin(forc), pin(E0), pin(Tg0)]
 diag = torch.empty((nmem, years, 3, 4), dtype=torch.float64).pin_memory()

@@ -7,7 +7,7 @@ from ebm_b200 import _lib
 
 nmem, years = int(sys.argv[1]), int(sys.argv[2])
 strict = len(sys.argv) > 3 and sys.argv[3] == "strict"
-st, par, forc, init = bench.miz_workload(ebm, nmem, 0, nmem, years)
+st, par, forc, init = bench.miz_workload(ebm, nmem, np.arange(nmem), years)
 lib = _lib.load()
 nx = st.nx
 fin = [np.empty((nmem, nx)) for _ in range(6)]

@@ -313,3 +313,24 @@ def test_sixteen_band_table_driven_instance(nx):
     assert_close(r.raw, o["raw"][sel], tol, "raw")
     assert_close(r.seasonal, o["seasonal"][sel], tol, "seasonal")
     assert_close(r.diag[..., :2], oracle_diag_classic(o["seasonal"], st.x)[..., :2], tol, "diag")
+
+
+@pytest.mark.parametrize("nx", [230, 250])
+def test_band_kernel_large_grids(nx):
+    """208 < nx <= 256: the band kernel (16 cells per band, 16 members per CTA).  nx = 230 needs 15 bands -- an odd
+    count, which the launcher pads to whole warps (no thread may shadow another thread's band)."""
+    nmem = 20
+    st = ebm.SpaceTime(nx, 2000, 2)
+    forcings = [ebm.Forcing(-8.0 + 16.0 * m / (nmem - 1)) for m in range(nmem)]
+    pars = [_par(B=2.0 + 0.05 * (m % 4)) for m in range(nmem)]
+    inits = [warm_init(nx) if m % 2 == 0 else cold_init(nx) for m in range(nmem)]
+    o = oracle_classic(st, forcings, pars, inits, raw=True, seasonal=True)
+    r = ebm.integrate_ensemble("Classic", st, forcings, pars, inits, field_stride=4)
+    assert r.flags.max() == 0
+    tol = 2e-8                                     # finer grids: see test_ensemble_diag_fields_and_state
+    assert_close(r.final["E"], o["E"], tol, "final E")
+    assert_close(r.final["Tg"], o["Tg"], tol, "final Tg")
+    sel = np.arange(0, nmem, 4)
+    assert_close(r.raw, o["raw"][sel], tol, "raw")
+    assert_close(r.seasonal, o["seasonal"][sel], tol, "seasonal")
+    assert_close(r.diag[..., :2], oracle_diag_classic(o["seasonal"], st.x)[..., :2], tol, "diag")

