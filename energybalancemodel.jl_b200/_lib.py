@@ -24,7 +24,7 @@ EXPORTED_SYMBOLS = (
     "ebm_version", "ebm_last_error", "ebm_device_count", "ebm_launch_count", "ebm_shutdown",
     "ebm_classic_run", "ebm_classic_run_device", "ebm_classic_step",
     "ebm_miz_run", "ebm_miz_run_device", "ebm_miz_step",
-    "ebm_transpose_device", "ebm_fp64_peak",
+    "ebm_transpose_device", "ebm_fp64_peak", "ebm_classic_run_multi", "ebm_miz_run_multi",
 )
 
 
@@ -62,6 +62,11 @@ class MizDeviceArgs(C.Structure):
                 ("flags", C.c_void_p)]
 
 
+class Multi(C.Structure):
+    _fields_ = [("ndevices", C.c_int32), ("diag_device", C.c_int32), ("packet", C.c_int32), ("reserved", C.c_int32),
+                ("devices", _i32p)]
+
+
 class EBMError(RuntimeError):
     def __init__(self, code: int, msg: str):
         super().__init__(f"libebm_cuda error {code}: {msg}")
@@ -97,6 +102,12 @@ def load():
     lib.ebm_miz_run_device.argtypes = [C.POINTER(Grid), C.POINTER(MizDeviceArgs), C.POINTER(Options), C.c_void_p]
     lib.ebm_miz_step.restype = C.c_int32
     lib.ebm_miz_step.argtypes = [C.POINTER(Grid), _dp, C.c_int32, C.c_double, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _i32p]
+    lib.ebm_classic_run_multi.restype = C.c_int32
+    lib.ebm_classic_run_multi.argtypes = [C.POINTER(Grid), C.c_int64, _dp, _dp, _dp, _dp, C.POINTER(Options), C.POINTER(Multi),
+                                          C.POINTER(ClassicOutputs)]
+    lib.ebm_miz_run_multi.restype = C.c_int32
+    lib.ebm_miz_run_multi.argtypes = [C.POINTER(Grid), C.c_int64, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, C.POINTER(Options),
+                                      C.POINTER(Multi), C.POINTER(MizOutputs)]
     lib.ebm_transpose_device.restype = C.c_int32
     lib.ebm_transpose_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]
     lib.ebm_fp64_peak.restype = C.c_int32
@@ -119,6 +130,17 @@ def make_grid(st) -> Grid:
     g = Grid(st.nx, st.nt, st.dur, st.grid_kind, st.winter.inx, st.summer.inx, dptr(st.x), dptr(st.t))
     g._keep = (st.x, st.t)  # keep the arrays alive as long as the struct
     return g
+
+
+def make_multi(ndevices=0, devices=None, diag_device=-1, packet=0) -> Multi:
+    """ebm_multi_t: GPUs of one *_run_multi call (0 = all visible), where the diagnostics go, packet size."""
+    arr = None
+    if devices is not None:
+        arr = (C.c_int32 * len(devices))(*devices)
+        ndevices = len(devices)
+    m = Multi(ndevices, diag_device, packet, 0, C.cast(arr, _i32p) if arr is not None else None)
+    m._keep = arr
+    return m
 
 
 def make_options(device=-1, lastonly=True, field_stride=0, strict=False, years_per_launch=0, newton_maxit=0,

@@ -569,10 +569,11 @@ __global__ void __maxnreg__(MAXR) classic_uniform_kernel(const ClassicKArgs a) {
   // which band pair a warp owns rotates with the CTA index: in a partially ice-covered member only the polar bands
   // take the expensive path, and without the rotation every resident CTA puts that warp on the same SM sub-partition
   constexpr int NWARP = WB * MW / 32;
-  const int wrot = (a.dbg & 4) ? warp : (int)((warp + blockIdx.x) % NWARP);
+  const long long bid = (long long)blockIdx.x + a.block0;   // 16-member group of this CTA
+  const int wrot = (a.dbg & 4) ? warp : (int)((warp + bid) % NWARP);
   const int band = WARPM ? (lane / (32 / WB)) : (wrot * BPW + lane / MW);
   const long long nmem = a.nmem;
-  const long long m_first = (long long)blockIdx.x * MW;
+  const long long m_first = bid * MW;
   const long long m_raw = m_first + mi;
   const bool active = m_raw < nmem;
   const long long m = active ? m_raw : nmem - 1;
@@ -734,7 +735,8 @@ int launch_uniform(const ClassicKArgs& a, cudaStream_t stream) {
   EBM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // leave room for several CTAs per SM: ask for the largest shared-memory carve-out (L1 is hardly used)
   EBM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  const long long blocks = (a.nmem + MW - 1) / MW;
+  const long long blocks = a.nblocks > 0 ? a.nblocks : (a.nmem + MW - 1) / MW - a.block0;
+  if (blocks <= 0) return EBM_OK;
   kern<<<(unsigned)blocks, WB * MW, smem, stream>>>(a);
   EBM_CUDA_TRY(cudaGetLastError());
   ebm_count_launch();
@@ -744,6 +746,18 @@ int launch_uniform(const ClassicKArgs& a, cudaStream_t stream) {
 }  // namespace
 
 int ebm_classic_uniform_max_nx() { return 208; }   // 8 bands of 13 cells up to nx = 104, 16 bands up to 208
+
+// resident CTAs of the production instantiation (nx <= 104) on the current device
+int ebm_classic_uniform_slots() {
+  int dev = 0, sms = 0, per_sm = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) { cudaGetLastError(); return 0; }
+  auto kern = classic_uniform_kernel<13, 8, 16, 168, true, false, true>;
+  const size_t smem = uniform_smem_bytes<13, 8, 16, true>(false);
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 8 * 16, smem) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return sms * per_sm;
+}
 
 // groups whose table-building parameters differ between members (e.g. a sweep over D): same mapping, coefficients
 // applied per member, every band eliminated in full

@@ -18,6 +18,7 @@
 // ----------------------------------------------------------------------------- errors / counters
 static thread_local char g_err[512] = "";
 static std::atomic<long long> g_launches{0};
+thread_local EbmDiagHook* ebm_tl_diag_hook = nullptr;
 
 void ebm_set_error(const char* fmt, ...) {
   va_list ap;
@@ -46,7 +47,8 @@ struct GridCacheEntry {
   EbmGridTables tabs;
 };
 std::mutex g_cache_mu;
-std::vector<GridCacheEntry> g_cache;
+std::vector<GridCacheEntry> g_cache;          // least recently used first
+constexpr size_t kMaxGridCache = 16;
 
 unsigned long long fnv1a(const void* p, size_t n, unsigned long long h = 1469598103934665603ULL) {
   const unsigned char* b = (const unsigned char*)p;
@@ -70,8 +72,14 @@ int get_tables(const ebm_grid_t* g, EbmGridTables* out, cudaStream_t stream) {
   unsigned long long h = fnv1a(g->x, sizeof(double) * g->nx);
   h = fnv1a(g->t, sizeof(double) * g->nt, h);
   std::lock_guard<std::mutex> lk(g_cache_mu);
-  for (auto& e : g_cache)
-    if (e.device == dev && e.nx == g->nx && e.nt == g->nt && e.kind == g->grid_kind && e.hash == h) { *out = e.tabs; return EBM_OK; }
+  for (size_t k = 0; k < g_cache.size(); ++k) {
+    auto& e = g_cache[k];
+    if (e.device == dev && e.nx == g->nx && e.nt == g->nt && e.kind == g->grid_kind && e.hash == h) {
+      *out = e.tabs;
+      if (k + 1 != g_cache.size()) { GridCacheEntry hit = e; g_cache.erase(g_cache.begin() + k); g_cache.push_back(hit); }   // most recent last
+      return EBM_OK;
+    }
+  }
   const int nx = g->nx, nt = g->nt;
   // layout: x, x2, lam_lo, lam_hi, wts [nx each]; ctab [nt+1]; diffx [nx+1]; mxxph, mxxmh, phmmh [nx each]
   const size_t n = (size_t)5 * nx + (nt + 1) + (nx + 1) + (size_t)3 * nx;
@@ -119,6 +127,17 @@ int get_tables(const ebm_grid_t* g, EbmGridTables* out, cudaStream_t stream) {
   e.tabs.x = dbuf; e.tabs.x2 = dbuf + nx; e.tabs.lam_lo = dbuf + 2 * nx; e.tabs.lam_hi = dbuf + 3 * nx;
   e.tabs.wts = dbuf + 4 * nx; e.tabs.ctab = dbuf + 5 * nx; e.tabs.diffx = e.tabs.ctab + nt + 1;
   e.tabs.mxxph = e.tabs.diffx + nx + 1; e.tabs.mxxmh = e.tabs.mxxph + nx; e.tabs.phmmh = e.tabs.mxxmh + nx;
+  // bounded: the least recently used entry goes when the cache is full.  Its tables may still be read by kernels in
+  // flight on other streams, so the block is released only after the device has drained.
+  if (g_cache.size() >= kMaxGridCache) {
+    int cur = 0;
+    cudaGetDevice(&cur);
+    cudaSetDevice(g_cache.front().device);
+    cudaDeviceSynchronize();
+    cudaFree(g_cache.front().dev);
+    cudaSetDevice(cur);
+    g_cache.erase(g_cache.begin());
+  }
   g_cache.push_back(e);
   *out = e.tabs;
   return EBM_OK;
@@ -130,6 +149,13 @@ ebm_options_t default_options() {
   o.device = -1; o.lastonly = 1;
   return o;
 }
+
+// Restores the caller's current CUDA device when an entry point returns (select_device may change it).
+struct DeviceRestore {
+  int prev = -1;
+  DeviceRestore() { if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); prev = -1; } }
+  ~DeviceRestore() { if (prev >= 0) cudaSetDevice(prev); }
+};
 
 int select_device(const ebm_options_t& o) {
   int n = 0;
@@ -192,6 +218,13 @@ struct DevBufs {
   }
 };
 
+// Owns the private stream of a host entry point.  Its destructor drains the stream before destroying it: an error
+// path must not hand the workspace blocks back (DevBufs, destroyed afterwards) while kernels or copies still use them.
+struct StreamGuard {
+  cudaStream_t s;
+  ~StreamGuard() { cudaStreamSynchronize(s); cudaStreamDestroy(s); cudaGetLastError(); }
+};
+
 #define EBM_TRY(expr) do { int _rc = (expr); if (_rc != EBM_OK) return _rc; } while (0)
 
 // host [rows][cols] -> device [cols][rows] via a staging buffer
@@ -221,6 +254,7 @@ extern "C" int32_t ebm_shutdown(void) {
   }
   cudaSetDevice(cur);
   cudaGetLastError();
+  ebm_multi_shutdown();
   return EBM_OK;
 }
 
@@ -232,6 +266,7 @@ extern "C" int32_t ebm_transpose_device(const double* src, double* dst, int64_t 
 extern "C" int32_t ebm_fp64_peak(int32_t device, double* tflops, double* sm_clock_mhz_est) {
   ebm_options_t o = default_options();
   o.device = device;
+  DeviceRestore _dr;
   EBM_TRY(select_device(o));
   return ebm_run_fp64_peak(-1, tflops, sm_clock_mhz_est);
 }
@@ -244,6 +279,7 @@ extern "C" int32_t ebm_classic_run_device(const ebm_grid_t* grid, const ebm_clas
   if (!args || !args->par || !args->forc || !args->E || !args->Tg) { ebm_set_error("classic_run_device: par, forc, E, Tg must be non-NULL"); return EBM_ERR_INVALID; }
   if (args->nmem < 1) { ebm_set_error("nmem must be >= 1"); return EBM_ERR_INVALID; }
   ebm_options_t opt = opt_in ? *opt_in : default_options();
+  DeviceRestore _dr;
   EBM_TRY(select_device(opt));
   if ((args->seasonal || args->raw) && opt.field_stride <= 0) { ebm_set_error("seasonal/raw output requested but field_stride == 0"); return EBM_ERR_INVALID; }
   if (opt.step_limit > 0) { ebm_set_error("step_limit is only supported by the MIZ path"); return EBM_ERR_UNSUPPORTED; }
@@ -260,6 +296,54 @@ extern "C" int32_t ebm_classic_run_device(const ebm_grid_t* grid, const ebm_clas
   a.dbg = getenv("EBM_DBG") ? atoi(getenv("EBM_DBG")) : 0;
   const int ypl = opt.years_per_launch > 0 ? opt.years_per_launch : grid->dur;
   static const int variant = getenv("EBM_CLASSIC_VARIANT") ? atoi(getenv("EBM_CLASSIC_VARIANT")) : 0;
+  // ---- wave balancing.  A CTA integrates 16 members for the whole run; the device holds `slots` CTAs at a time.
+  // 8192 members (the 8-GPU share of the 65 536-member sweep) are 512 CTAs on 444 slots: one launch runs them as
+  // two waves, the second 15 % full.  Cut instead into 8 ranges of CTAs on 8 streams, each advancing in chunks of
+  // years: whenever a range finishes a chunk its slots go to whichever range is waiting, and the makespan
+  // approaches work / slots.  Results are bit-identical (a CTA's arithmetic does not depend on the launch shape).
+  if (!opt.strict && variant >= 0 && variant < 20 && a.nx <= 104 && !getenv("EBM_NO_WAVE_BALANCE")) {
+    const long long blocks = (a.nmem + 15) / 16;
+    const long long slots = ebm_classic_uniform_slots();
+    const long long waves = slots > 0 ? (blocks + slots - 1) / slots : 0;
+    if (slots > 0 && blocks > slots && blocks <= 12 * slots && grid->dur >= 8 &&
+        (double)(waves * slots) > 1.08 * (double)blocks) {
+      constexpr int S = 8;
+      const int chunk = std::min(ypl, std::max(1, grid->dur / 16));
+      a.uniform_split = 1;
+      cudaEvent_t fork;
+      EBM_CUDA_TRY(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
+      EBM_CUDA_TRY(cudaEventRecord(fork, stream));
+      int rc = EBM_OK;
+      cudaStream_t aux[S];
+      cudaEvent_t done[S];
+      int made = 0;
+      for (; made < S && rc == EBM_OK; ++made) {
+        if (cudaStreamCreateWithFlags(&aux[made], cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&done[made], cudaEventDisableTiming) != cudaSuccess) { rc = EBM_ERR_CUDA; ebm_set_error("wave balancing: stream creation failed"); break; }
+        if (cudaStreamWaitEvent(aux[made], fork, 0) != cudaSuccess) rc = EBM_ERR_CUDA;
+      }
+      for (int y0 = 0; y0 < grid->dur && rc == EBM_OK; y0 += chunk) {
+        for (int q = 0; q < made && rc == EBM_OK; ++q) {
+          ClassicKArgs b = a;
+          b.year0 = y0;
+          b.nyears = std::min(chunk, grid->dur - y0);
+          b.block0 = blocks * q / made;
+          b.nblocks = blocks * (q + 1) / made - b.block0;
+          if (b.nblocks <= 0) continue;
+          rc = ebm_launch_classic_uniform(b, variant, aux[q]);
+          if (rc == EBM_OK) rc = ebm_launch_classic_general(b, aux[q]);
+        }
+      }
+      for (int q = 0; q < made; ++q) {   // join (and release: destruction is deferred until the work has drained)
+        cudaEventRecord(done[q], aux[q]);
+        cudaStreamWaitEvent(stream, done[q], 0);
+        cudaEventDestroy(done[q]);
+        cudaStreamDestroy(aux[q]);
+      }
+      cudaEventDestroy(fork);
+      return rc;
+    }
+  }
   for (int y0 = 0; y0 < grid->dur; y0 += ypl) {
     a.year0 = y0;
     a.nyears = (y0 + ypl <= grid->dur) ? ypl : grid->dur - y0;
@@ -294,6 +378,7 @@ extern "C" int32_t ebm_classic_run(const ebm_grid_t* grid, int64_t nmem, const e
   EBM_TRY(check_grid(grid));
   if (nmem < 1 || !par || !forc || !E0 || !Tg0 || !out) { ebm_set_error("classic_run: nmem >= 1 and par, forc, E0, Tg0, out must be non-NULL"); return EBM_ERR_INVALID; }
   ebm_options_t opt = opt_in ? *opt_in : default_options();
+  DeviceRestore _dr;
   EBM_TRY(select_device(opt));
   if ((out->seasonal || out->raw) && opt.field_stride <= 0) { ebm_set_error("seasonal/raw output requested but field_stride == 0"); return EBM_ERR_INVALID; }
   const int nx = grid->nx, nt = grid->nt, dur = grid->dur;
@@ -301,8 +386,8 @@ extern "C" int32_t ebm_classic_run(const ebm_grid_t* grid, int64_t nmem, const e
   const long long nraw = opt.lastonly ? nt : (long long)nt * dur;
   cudaStream_t s;
   EBM_CUDA_TRY(cudaStreamCreate(&s));
-  struct StreamGuard { cudaStream_t s; ~StreamGuard() { cudaStreamDestroy(s); } } sg{s};
-  DevBufs B;
+  DevBufs B;                 // declared first: destroyed last
+  StreamGuard sg{s};         // ... after the stream has drained (error paths return without a synchronise of their own)
   double *stage, *dpar, *dforc, *dE, *dTg, *ddiag = nullptr, *dseas = nullptr, *draw = nullptr;
   int* dflags = nullptr;
   const size_t stage_n = (size_t)nmem * (nx > EBM_CLASSIC_NPAR ? nx : EBM_CLASSIC_NPAR);
@@ -381,7 +466,10 @@ extern "C" int32_t ebm_classic_run(const ebm_grid_t* grid, int64_t nmem, const e
   da.diag = ddiag; da.seasonal = dseas; da.raw = draw; da.flags = dflags;
   da.member_index = (const int64_t*)dperm;
   EBM_TRY(ebm_classic_run_device(grid, &da, &opt, s));
-  if (out->diag) EBM_CUDA_TRY(cudaMemcpyAsync(out->diag, ddiag, sizeof(double) * ndiag, cudaMemcpyDeviceToHost, s));
+  if (out->diag) {
+    if (ebm_tl_diag_hook) EBM_TRY(ebm_tl_diag_hook->consume(ddiag, ndiag, s));
+    else EBM_CUDA_TRY(cudaMemcpyAsync(out->diag, ddiag, sizeof(double) * ndiag, cudaMemcpyDeviceToHost, s));
+  }
   if (out->seasonal) EBM_CUDA_TRY(cudaMemcpyAsync(out->seasonal, dseas, sizeof(double) * nseas, cudaMemcpyDeviceToHost, s));
   if (out->raw) EBM_CUDA_TRY(cudaMemcpyAsync(out->raw, draw, sizeof(double) * nrawn, cudaMemcpyDeviceToHost, s));
   if (out->flags) EBM_CUDA_TRY(cudaMemcpyAsync(out->flags, dflags, sizeof(int) * nmem, cudaMemcpyDeviceToHost, s));
@@ -397,6 +485,7 @@ extern "C" int32_t ebm_classic_step(const ebm_grid_t* grid, const ebm_classic_pa
   if (!par || !E || !Tg || !T || !h) { ebm_set_error("classic_step: NULL argument"); return EBM_ERR_INVALID; }
   if (ti < 1 || ti > grid->nt) { ebm_set_error("classic_step: ti=%d outside 1..nt", ti); return EBM_ERR_INVALID; }
   ebm_options_t opt = default_options();
+  DeviceRestore _dr;
   EBM_TRY(select_device(opt));
   const int nx = grid->nx;
   EbmGridTables tabs;
@@ -427,6 +516,7 @@ extern "C" int32_t ebm_miz_run_device(const ebm_grid_t* grid, const ebm_miz_devi
   }
   if (args->nmem < 1) { ebm_set_error("nmem must be >= 1"); return EBM_ERR_INVALID; }
   ebm_options_t opt = opt_in ? *opt_in : default_options();
+  DeviceRestore _dr;
   EBM_TRY(select_device(opt));
   if ((args->seasonal || args->raw) && opt.field_stride <= 0) { ebm_set_error("seasonal/raw output requested but field_stride == 0"); return EBM_ERR_INVALID; }
   MizKArgs a;
@@ -459,6 +549,7 @@ extern "C" int32_t ebm_miz_run(const ebm_grid_t* grid, int64_t nmem, const ebm_m
   EBM_TRY(check_grid(grid));
   if (nmem < 1 || !par || !forc || !Ei0 || !Ew0 || !h0 || !D0 || !phi0 || !out) { ebm_set_error("miz_run: NULL argument or nmem < 1"); return EBM_ERR_INVALID; }
   ebm_options_t opt = opt_in ? *opt_in : default_options();
+  DeviceRestore _dr;
   EBM_TRY(select_device(opt));
   if ((out->seasonal || out->raw) && opt.field_stride <= 0) { ebm_set_error("seasonal/raw output requested but field_stride == 0"); return EBM_ERR_INVALID; }
   const int nx = grid->nx, nt = grid->nt, dur = grid->dur;
@@ -466,8 +557,8 @@ extern "C" int32_t ebm_miz_run(const ebm_grid_t* grid, int64_t nmem, const ebm_m
   const long long nraw = opt.lastonly ? nt : (long long)nt * dur;
   cudaStream_t s;
   EBM_CUDA_TRY(cudaStreamCreate(&s));
-  struct StreamGuard { cudaStream_t s; ~StreamGuard() { cudaStreamDestroy(s); } } sg{s};
-  DevBufs B;
+  DevBufs B;                 // declared first: destroyed last
+  StreamGuard sg{s};         // ... after the stream has drained (error paths return without a synchronise of their own)
   double *stage, *dpar, *dforc, *dst[6], *ddiag = nullptr, *dseas = nullptr, *draw = nullptr;
   long long *dit = nullptr, *dnc = nullptr;
   int* dflags = nullptr;
@@ -500,7 +591,10 @@ extern "C" int32_t ebm_miz_run(const ebm_grid_t* grid, int64_t nmem, const ebm_m
   da.diag = ddiag; da.seasonal = dseas; da.raw = draw;
   da.newton_iters = (int64_t*)dit; da.nonconv = (int64_t*)dnc; da.flags = dflags;
   EBM_TRY(ebm_miz_run_device(grid, &da, &opt, s));
-  if (out->diag) EBM_CUDA_TRY(cudaMemcpyAsync(out->diag, ddiag, sizeof(double) * ndiag, cudaMemcpyDeviceToHost, s));
+  if (out->diag) {
+    if (ebm_tl_diag_hook) EBM_TRY(ebm_tl_diag_hook->consume(ddiag, ndiag, s));
+    else EBM_CUDA_TRY(cudaMemcpyAsync(out->diag, ddiag, sizeof(double) * ndiag, cudaMemcpyDeviceToHost, s));
+  }
   if (out->seasonal) EBM_CUDA_TRY(cudaMemcpyAsync(out->seasonal, dseas, sizeof(double) * nseas, cudaMemcpyDeviceToHost, s));
   if (out->raw) EBM_CUDA_TRY(cudaMemcpyAsync(out->raw, draw, sizeof(double) * nrawn, cudaMemcpyDeviceToHost, s));
   if (out->newton_iters) EBM_CUDA_TRY(cudaMemcpyAsync(out->newton_iters, dit, sizeof(long long) * nmem, cudaMemcpyDeviceToHost, s));
@@ -520,6 +614,7 @@ extern "C" int32_t ebm_miz_step(const ebm_grid_t* grid, const ebm_miz_params_t* 
   if (!par || !Ei || !Ew || !h || !D || !phi || !T0 || !vars_out) { ebm_set_error("miz_step: NULL argument"); return EBM_ERR_INVALID; }
   if (ti < 1 || ti > grid->nt) { ebm_set_error("miz_step: ti=%d outside 1..nt", ti); return EBM_ERR_INVALID; }
   ebm_options_t opt = default_options();
+  DeviceRestore _dr;
   EBM_TRY(select_device(opt));
   const int nx = grid->nx;
   EbmGridTables tabs;

@@ -19,6 +19,18 @@ void ebm_count_launch(int n = 1);
     }                                                                                             \
   } while (0)
 
+// ----------------------------------------------------------------------------- multi-device hook (ebm_multi.cu)
+// While set (thread local), the host entry points hand the device-resident diagnostics of their run to the hook
+// instead of copying them to out->diag: ebm_*_run_multi uses it to send them to another GPU over NCCL.
+struct EbmDiagHook {
+  virtual int consume(const double* ddiag, size_t count, cudaStream_t stream) = 0;   // EBM_* status
+  virtual ~EbmDiagHook() {}
+};
+extern thread_local EbmDiagHook* ebm_tl_diag_hook;
+int ebm_launch_scatter_rows(const double* src, double* dst, long long nrows, long long rowlen, const long long* idx,
+                            cudaStream_t stream);   // dst[idx[r]][:] = src[r][:]
+void ebm_multi_shutdown();   // destroys the NCCL communicators of ebm_multi.cu
+
 // ----------------------------------------------------------------------------- device grid tables
 // Everything that depends only on SpaceTime (x, t, nx, nt), computed once on the host in IEEE
 // double with the reference's association order, cached per device (ebm_capi.cu).
@@ -52,6 +64,7 @@ struct ClassicKArgs {
   double* diag; double* seasonal; double* raw; int* flags;
   const long long* orig;         // NULL or [nmem]: original member index of slot m (output rows, field selection)
   int dbg;                       // development switches (env EBM_DBG)
+  long long block0, nblocks;     // classic_uniform.cu: this launch covers the 16-member groups [block0, block0 + nblocks); nblocks 0 = all
 };
 
 struct MizKArgs {
@@ -78,6 +91,7 @@ int ebm_launch_classic_general(const ClassicKArgs& a, cudaStream_t stream);
 int ebm_launch_classic_fused(const ClassicKArgs& a, int variant, cudaStream_t stream);          // classic_fused.cu
 int ebm_launch_classic_fused_general(const ClassicKArgs& a, cudaStream_t stream);
 int ebm_classic_uniform_max_nx();
+int ebm_classic_uniform_slots();   // resident CTAs of the production kernel on the current device (wave balancing)
 int ebm_launch_classic_strict(const ClassicKArgs& a, cudaStream_t stream);
 int ebm_launch_classic_single_step(const EbmGridTables& g, const double* par15, int ti, double f,
                                    double* E, double* Tg, double* T, double* h, cudaStream_t stream);

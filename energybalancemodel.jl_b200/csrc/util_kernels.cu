@@ -32,6 +32,16 @@ __global__ void gather_transpose_kernel(const double* __restrict__ src, double* 
   }
 }
 
+// dst[idx[r]][:] = src[r][:]  (rows of `rowlen` doubles)
+__global__ void scatter_rows_kernel(const double* __restrict__ src, double* __restrict__ dst, long long nrows, long long rowlen,
+                                    const long long* __restrict__ idx) {
+  const long long n = nrows * rowlen;
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (long long)gridDim.x * blockDim.x) {
+    const long long r = q / rowlen, c = q % rowlen;
+    dst[idx[r] * rowlen + c] = src[q];
+  }
+}
+
 __global__ void fill_kernel(double* dst, long long n, double v) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     dst[i] = v;
@@ -71,6 +81,15 @@ int ebm_launch_gather_transpose(const double* src, double* dst, long long rows, 
                                 int inverse, cudaStream_t stream) {
   if (rows <= 0 || cols <= 0) return EBM_OK;
   gather_transpose_kernel<<<1184, 256, 0, stream>>>(src, dst, rows, cols, idx, inverse);
+  EBM_CUDA_TRY(cudaGetLastError());
+  ebm_count_launch();
+  return EBM_OK;
+}
+
+int ebm_launch_scatter_rows(const double* src, double* dst, long long nrows, long long rowlen, const long long* idx,
+                            cudaStream_t stream) {
+  if (nrows <= 0 || rowlen <= 0) return EBM_OK;
+  scatter_rows_kernel<<<1184, 256, 0, stream>>>(src, dst, nrows, rowlen, idx);
   EBM_CUDA_TRY(cudaGetLastError());
   ebm_count_launch();
   return EBM_OK;

@@ -106,11 +106,15 @@ def integrate_arrays(model, st: SpaceTime, forc, par, state, *, lastonly: bool =
                      want_diag: bool = True, want_seasonal: bool | None = None, want_raw: bool | None = None,
                      device: int = -1, strict: bool = False, years_per_launch: int = 0,
                      newton_tol: float = 0.0, newton_maxit: int = 0, step_limit: int = 0,
-                     start_year: int = 0) -> EnsembleResult:
+                     start_year: int = 0, devices=None, packet: int = 0) -> EnsembleResult:
     """Array form for large ensembles (no per-member Python objects): ``forc[nmem, 10]`` (``Forcing.row()`` layout),
     ``par[nmem, 15 | 22]`` in ``CLASSIC_PAR_ORDER`` / ``MIZ_PAR_ORDER``, ``state`` a dict of ``[nmem, nx]`` arrays
     (classic ``E, Tg``; MIZ ``Ei, Ew, h, D, phi`` and optionally the closure warm start ``T0``) -- exactly the buffers
-    of ``ebm_classic_run`` / ``ebm_miz_run`` (include/ebm_cuda.h)."""
+    of ``ebm_classic_run`` / ``ebm_miz_run`` (include/ebm_cuda.h).
+
+    ``devices``: a list of CUDA ordinals (or an int n = the first n devices, 0 = all) runs the ensemble on several
+    GPUs through ``ebm_classic_run_multi`` / ``ebm_miz_run_multi``: one host thread + stream per GPU inside the
+    library, members dealt in ``packet``-member packets (default 32) after a sort by cost; no field outputs."""
     name = model_name(model)
     lib = _lib.load()
     nx, nt, dur = st.nx, st.nt, st.dur
@@ -134,6 +138,11 @@ def integrate_arrays(model, st: SpaceTime, forc, par, state, *, lastonly: bool =
     grid = _lib.make_grid(st)
     opt = _lib.make_options(device, lastonly, field_stride, strict, years_per_launch, newton_maxit, newton_tol,
                             step_limit, start_year)
+    multi = None
+    if devices is not None:
+        if field_stride > 0:
+            raise ValueError("field outputs (field_stride > 0) are single-GPU options")
+        multi = _lib.make_multi(devices=list(devices), packet=packet) if not isinstance(devices, int) else _lib.make_multi(ndevices=devices, packet=packet)
     nsel = (nmem + field_stride - 1) // field_stride if field_stride > 0 else 0
     nraw = nt if lastonly else nt * dur
     if want_seasonal is None:
@@ -152,8 +161,12 @@ def integrate_arrays(model, st: SpaceTime, forc, par, state, *, lastonly: bool =
         res.final = {"E": np.empty((nmem, nx)), "Tg": np.empty((nmem, nx))}
         out = _lib.ClassicOutputs(_lib.dptr(res.diag), _lib.dptr(res.seasonal), _lib.dptr(res.raw),
                                   _lib.dptr(res.final["E"]), _lib.dptr(res.final["Tg"]), flags_p)
-        _lib.check(lib.ebm_classic_run(C.byref(grid), nmem, _lib.dptr(par), _lib.dptr(forc), _lib.dptr(arrs["E"]),
-                                       _lib.dptr(arrs["Tg"]), C.byref(opt), C.byref(out)))
+        if multi is not None:
+            _lib.check(lib.ebm_classic_run_multi(C.byref(grid), nmem, _lib.dptr(par), _lib.dptr(forc), _lib.dptr(arrs["E"]),
+                                                 _lib.dptr(arrs["Tg"]), C.byref(opt), C.byref(multi), C.byref(out)))
+        else:
+            _lib.check(lib.ebm_classic_run(C.byref(grid), nmem, _lib.dptr(par), _lib.dptr(forc), _lib.dptr(arrs["E"]),
+                                           _lib.dptr(arrs["Tg"]), C.byref(opt), C.byref(out)))
     else:
         res.final = {k: np.empty((nmem, nx)) for k in _MIZ_STATE + ("T0",)}
         res.newton_iters = np.zeros(nmem, dtype=np.int64)
@@ -162,8 +175,13 @@ def integrate_arrays(model, st: SpaceTime, forc, par, state, *, lastonly: bool =
                               *[_lib.dptr(res.final[k]) for k in _MIZ_STATE + ("T0",)],
                               res.newton_iters.ctypes.data_as(C.POINTER(C.c_int64)),
                               res.nonconv.ctypes.data_as(C.POINTER(C.c_int64)), flags_p)
-        _lib.check(lib.ebm_miz_run(C.byref(grid), nmem, _lib.dptr(par), _lib.dptr(forc), *[_lib.dptr(arrs[k]) for k in _MIZ_STATE],
-                                   _lib.dptr(arrs.get("T0")), C.byref(opt), C.byref(out)))
+        if multi is not None:
+            _lib.check(lib.ebm_miz_run_multi(C.byref(grid), nmem, _lib.dptr(par), _lib.dptr(forc),
+                                             *[_lib.dptr(arrs[k]) for k in _MIZ_STATE], _lib.dptr(arrs.get("T0")),
+                                             C.byref(opt), C.byref(multi), C.byref(out)))
+        else:
+            _lib.check(lib.ebm_miz_run(C.byref(grid), nmem, _lib.dptr(par), _lib.dptr(forc), *[_lib.dptr(arrs[k]) for k in _MIZ_STATE],
+                                       _lib.dptr(arrs.get("T0")), C.byref(opt), C.byref(out)))
     return res
 
 
@@ -206,6 +224,10 @@ def step(model, t: float, f: float, vars: Collection, st: SpaceTime, par: Collec
                                         _lib.dptr(T), _lib.dptr(h)))
         vars["E"], vars["Tg"], vars["T"], vars["h"] = E, Tg, T, h
     else:
+        # the reference's MIZ step! uses t itself (cos(2 pi t), src/miz.jl:11), not a table index: the device entry
+        # point takes the index of t in st.t, so a t off the grid would silently get its neighbour's insolation
+        if not (1 <= ti <= st.nt) or abs(float(st.t[ti - 1]) - float(t)) > 1e-12:
+            raise ValueError(f"MIZ step: t = {t!r} is not one of st.t (nearest: st.t[{ti - 1}] = {float(st.t[max(min(ti, st.nt), 1) - 1])!r})")
         p = _rows([par], MIZ_PAR_ORDER)[0]
         stt = [np.array(vars[k], dtype=np.float64) for k in _MIZ_STATE]
         T0 = np.array(vars["T0"], dtype=np.float64) if "T0" in vars else np.zeros(nx)

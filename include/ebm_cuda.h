@@ -153,7 +153,7 @@ const char* ebm_last_error(void);
 int32_t ebm_device_count(void);
 /* number of kernels this library has launched so far in this process (for bench accounting) */
 int64_t ebm_launch_count(void);
-/* release cached device tables */
+/* release cached device tables, the workspace, and the NCCL communicators of the *_multi entry points */
 int32_t ebm_shutdown(void);
 
 /* ---- classic: integrate(:Classic, st, forcing[], par[], init[]) for nmem members ----------------
@@ -182,6 +182,30 @@ int32_t ebm_miz_run_device(const ebm_grid_t* grid, const ebm_miz_device_args_t* 
 int32_t ebm_miz_step(const ebm_grid_t* grid, const ebm_miz_params_t* par, int32_t ti, double f,
                      double* Ei, double* Ew, double* h, double* D, double* phi, double* T0,
                      double* vars_out, int32_t* newton_iters);
+
+/* ---- several GPUs behind one call ------------------------------------------------
+ * Members are independent (src/infrastructure.jl:615-636 integrates one member; nothing couples two), so the path
+ * shards with no data-path collective.  Single process, one host thread + stream per GPU; members are dealt to
+ * the GPUs in packets after a stable sort by what they cost (classic: regime of the initial state).  Every output
+ * row comes back at the member's original index.  seasonal / raw (per-member field outputs) must be NULL.       */
+typedef struct ebm_multi {
+  int32_t ndevices;       /* GPUs to use; 0 = every visible device */
+  int32_t diag_device;    /* -1: out->diag is host memory, every GPU copies its own rows back;
+                             >= 0: out->diag is DEVICE memory on that ordinal (one of `devices`), pre-filled by the
+                             caller; the other GPUs send their rows there over NVLink -- ncclSend/ncclRecv on
+                             communicators the library owns (created lazily, destroyed by ebm_shutdown) */
+  int32_t packet;         /* members per dealt packet, 0 -> 32 */
+  int32_t reserved;
+  const int32_t* devices; /* NULL = ordinals 0 .. ndevices-1 */
+} ebm_multi_t;
+int32_t ebm_classic_run_multi(const ebm_grid_t* grid, int64_t nmem, const ebm_classic_params_t* par,
+                              const ebm_forcing_t* forc, const double* E0, const double* Tg0,
+                              const ebm_options_t* opt /* opt->device is ignored */, const ebm_multi_t* multi,
+                              ebm_classic_outputs_t* out);
+int32_t ebm_miz_run_multi(const ebm_grid_t* grid, int64_t nmem, const ebm_miz_params_t* par,
+                          const ebm_forcing_t* forc, const double* Ei0, const double* Ew0, const double* h0,
+                          const double* D0, const double* phi0, const double* T0guess /* NULL = zeros */,
+                          const ebm_options_t* opt, const ebm_multi_t* multi, ebm_miz_outputs_t* out);
 
 /* ---- layout helpers (device, on `stream`): [rows][cols] -> [cols][rows] ---------------------------- */
 int32_t ebm_transpose_device(const double* src, double* dst, int64_t rows, int64_t cols, void* stream);

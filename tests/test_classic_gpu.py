@@ -334,3 +334,83 @@ def test_band_kernel_large_grids(nx):
     assert_close(r.raw, o["raw"][sel], tol, "raw")
     assert_close(r.seasonal, o["seasonal"][sel], tol, "seasonal")
     assert_close(r.diag[..., :2], oracle_diag_classic(o["seasonal"], st.x)[..., :2], tol, "diag")
+
+
+def _ndev():
+    return ebm._lib.load().ebm_device_count()
+
+
+@pytest.mark.parametrize("diag_on_device", [False, True])
+def test_multi_gpu_entry_point_matches_single_gpu_bitwise(diag_on_device):
+    """ebm_classic_run_multi (one host thread + stream per GPU inside the library, members dealt in packets after the
+    regime sort): every output row equals the single-GPU call's bit for bit.  With diag_on_device the diagnostics of
+    the other GPU arrive in device memory of GPU 0 over NCCL (communicator owned by the library).  Runs on one GPU
+    too (one device = the degenerate deal)."""
+    import ctypes as C
+    import torch
+    from ebm_b200 import _lib
+    ndev = min(_ndev(), 2)
+    nmem, nx, years = 200, 100, 2
+    st = ebm.SpaceTime(nx, 2000, years)
+    p = _par()
+    par = np.tile([p[k] for k in ebm.CLASSIC_PAR_ORDER], (nmem, 1))
+    forc = np.zeros((nmem, 10)); forc[:, :3] = np.linspace(-15.0, 15.0, nmem)[:, None]
+    warm = (np.arange(nmem) % 3) != 0
+    state = {"E": np.where(warm[:, None], 98.0, -9.5) * np.ones((nmem, nx)), "Tg": np.where(warm[:, None], 10.0, -10.0) * np.ones((nmem, nx))}
+    ref = ebm.integrate_arrays("Classic", st, forc, par, state)
+    if not diag_on_device:
+        r = ebm.integrate_arrays("Classic", st, forc, par, state, devices=list(range(ndev)), packet=16)
+        assert np.array_equal(r.diag, ref.diag)
+    else:
+        lib = _lib.load()
+        d_diag = torch.full((nmem, years, 3, 4), float("nan"), dtype=torch.float64, device="cuda:0")
+        E_fin, Tg_fin = np.empty((nmem, nx)), np.empty((nmem, nx))
+        flags = np.zeros(nmem, dtype=np.int32)
+        out = _lib.ClassicOutputs(C.cast(d_diag.data_ptr(), C.POINTER(C.c_double)), None, None, _lib.dptr(E_fin), _lib.dptr(Tg_fin),
+                                  flags.ctypes.data_as(C.POINTER(C.c_int32)))
+        grid, opt = _lib.make_grid(st), _lib.make_options()
+        multi = _lib.make_multi(devices=list(range(ndev)), diag_device=0, packet=16)
+        _lib.check(lib.ebm_classic_run_multi(C.byref(grid), nmem, _lib.dptr(np.ascontiguousarray(par)), _lib.dptr(np.ascontiguousarray(forc)),
+                                             _lib.dptr(state["E"]), _lib.dptr(state["Tg"]), C.byref(opt), C.byref(multi), C.byref(out)))
+        torch.cuda.synchronize()
+        assert np.array_equal(d_diag.cpu().numpy(), ref.diag)
+
+        class R: pass
+        r = R(); r.final = {"E": E_fin, "Tg": Tg_fin}; r.flags = flags
+    assert np.array_equal(r.final["E"], ref.final["E"]) and np.array_equal(r.final["Tg"], ref.final["Tg"])
+    assert np.array_equal(r.flags, ref.flags)
+
+
+def test_wave_balanced_launch_is_bit_identical():
+    """A member count that leaves the last wave of CTAs nearly empty takes the wave-balanced launch (ranges of CTAs on
+    several streams, advancing in chunks of years): bit-identical to one launch."""
+    import os, subprocess, sys
+    code = r"""
+import sys, numpy as np
+sys.path.insert(0, %r)
+import ebm_b200 as ebm
+lib = ebm._lib.load()
+slots = 148 * 3
+nmem, nx, years = (slots + 40) * 16, 100, 8
+st = ebm.SpaceTime(nx, 2000, years)
+p = ebm.default_parameters("Classic")
+par = np.tile([p[k] for k in ebm.CLASSIC_PAR_ORDER], (nmem, 1))
+forc = np.zeros((nmem, 10)); forc[:, :3] = np.linspace(-18.0, 18.0, nmem)[:, None]
+warm = (np.arange(nmem) %% 2) == 0
+state = {"E": np.where(warm[:, None], 98.0, -9.5) * np.ones((nmem, nx)), "Tg": np.where(warm[:, None], 10.0, -10.0) * np.ones((nmem, nx))}
+n0 = lib.ebm_launch_count()
+r = ebm.integrate_arrays("Classic", st, forc, par, state)
+print("LAUNCHES", lib.ebm_launch_count() - n0)
+np.save(sys.argv[1], np.concatenate([r.final["E"].ravel(), r.final["Tg"].ravel(), np.nan_to_num(r.diag).ravel()]))
+""" % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))),)
+    import tempfile
+    with tempfile.TemporaryDirectory() as tmp:
+        outs = []
+        for tag, env in (("a", {}), ("b", {"EBM_NO_WAVE_BALANCE": "1"})):
+            path = os.path.join(tmp, tag + ".npy")
+            r = subprocess.run([sys.executable, "-c", code, path], env=dict(os.environ, **env), capture_output=True, text=True)
+            assert r.returncode == 0, r.stderr[-2000:]
+            outs.append((np.load(path), int(r.stdout.split("LAUNCHES")[1].split()[0])))
+        (a, la), (b, lb) = outs
+        assert np.array_equal(a, b)
+        assert la > lb    # the balanced path really ran: many chunked launches instead of a few

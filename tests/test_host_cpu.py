@@ -288,3 +288,32 @@ def test_world_size_two_dealt_gather_over_gloo(total, tmp_path):
     outs = [p.communicate(timeout=240)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert f"DEAL_GATHER_OK {total}" in outs[0]
+
+
+def test_multi_struct_layout_and_no_gpu_behaviour():
+    """ebm_multi_t mirrors the header; without a device the multi-GPU entry points fail loudly like the others."""
+    exe = os.path.join(ROOT, "tests", "_layout_probe_multi")
+    code = r"""
+#include <stdio.h>
+#include <stddef.h>
+#include "ebm_cuda.h"
+int main(void) { printf("%zu %zu %zu %zu\n", sizeof(ebm_multi_t), offsetof(ebm_multi_t, diag_device), offsetof(ebm_multi_t, packet), offsetof(ebm_multi_t, devices)); return 0; }"""
+    r = subprocess.run(["gcc", "-x", "c", "-", "-I", os.path.join(ROOT, "include"), "-o", exe], input=code, text=True, capture_output=True)
+    assert r.returncode == 0, r.stderr
+    try:
+        got = list(map(int, subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()))
+    finally:
+        os.remove(exe)
+    assert got == [C.sizeof(_lib.Multi), _lib.Multi.diag_device.offset, _lib.Multi.packet.offset, _lib.Multi.devices.offset]
+    if _no_gpu():
+        st = ebm.SpaceTime(100, 2000, 1)
+        p = ebm.default_parameters("Classic")
+        par = np.tile([p[k] for k in ebm.CLASSIC_PAR_ORDER], (4, 1))
+        forc = np.zeros((4, 10))
+        state = {"E": np.full((4, 100), 98.0), "Tg": np.full((4, 100), 10.0)}
+        with pytest.raises(_lib.EBMError) as ei:
+            ebm.integrate_arrays("Classic", st, forc, par, state, devices=[0, 1])
+        assert ei.value.code == _lib.EBM_ERR_CUDA
+    with pytest.raises(ValueError):
+        ebm.integrate_arrays("Classic", ebm.SpaceTime(100, 2000, 1), np.zeros((1, 10)), np.zeros((1, 15)),
+                             {"E": np.zeros((1, 100)), "Tg": np.zeros((1, 100))}, devices=[0], field_stride=1)
