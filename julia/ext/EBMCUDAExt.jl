@@ -40,6 +40,9 @@ struct COptions
     device::Int32; lastonly::Int32; field_stride::Int32; strict::Int32; years_per_launch::Int32
     newton_maxit::Int32; newton_tol::Float64; step_limit::Int32; start_year::Int32
 end
+struct CMulti          # ebm_multi_t
+    ndevices::Int32; diag_device::Int32; packet::Int32; reserved::Int32; devices::Ptr{Int32}
+end
 struct CClassicOutputs
     diag::Ptr{Float64}; seasonal::Ptr{Float64}; raw::Ptr{Float64}; E_final::Ptr{Float64}; Tg_final::Ptr{Float64}
     flags::Ptr{Int32}
@@ -74,11 +77,16 @@ the per-member-year scalar diagnostics `diag[4, 3, dur, nmem]`, final states, fl
 function integrate(model::Symbol, st::SpaceTime{F}, forcings::AbstractVector{<:Forcing},
                    pars::AbstractVector{Collection{Float64}}, inits::AbstractVector{Collection{Vec}};
                    lastonly::Bool=true, field_stride::Int=1, debug::Union{Expr,Nothing}=nothing,
-                   verbose::Bool=false, device::Int=-1) where F
+                   verbose::Bool=false, device::Int=-1, devices::Union{Nothing,AbstractVector{<:Integer}}=nothing) where F
     isnothing(debug) || throw(ArgumentError("`debug::Expr` cannot be evaluated on the device"))
     model in (:Classic, :MIZ) || throw(MethodError(EBM.Infrastructure.step!, (Val(model),)))
     nmem = length(pars)
     (nmem > 0 && length(forcings) == nmem == length(inits)) || throw(ArgumentError("forcings, pars, inits must have equal non-zero length"))
+    # devices = [0, 1, ...]: several GPUs behind one call (ebm_*_run_multi: one host thread + stream per GPU inside
+    # the library, members dealt in 32-member packets after a sort by cost); diagnostics, final state and flags only
+    multi = !isnothing(devices)
+    multi && (field_stride = 0)
+    devs = multi ? Int32.(collect(devices)) : Int32[]
     nx, nt, dur = st.nx, st.nt, st.dur
     nsel = field_stride > 0 ? cld(nmem, field_stride) : 0
     nraw = lastonly ? nt : nt * dur
@@ -92,7 +100,8 @@ function integrate(model::Symbol, st::SpaceTime{F}, forcings::AbstractVector{<:F
     x, t = st.x, st.t
     opt = Ref(COptions(device, lastonly, field_stride, 0, 0, 0, 0.0, 0, 0))
     local final, stats
-    GC.@preserve x t forc diag seasonal raw flags begin
+    GC.@preserve x t forc diag seasonal raw flags devs begin
+        mopt = Ref(CMulti(length(devs), -1, 0, 0, multi ? pointer(devs) : Ptr{Int32}(C_NULL)))
         grid = Ref(CGrid(nx, nt, dur, grid_kind(st), st.winter.inx, st.summer.inx, pointer(x), pointer(t)))
         sp = nsel > 0 ? pointer(seasonal) : Ptr{Float64}(C_NULL)
         rp = nsel > 0 ? pointer(raw) : Ptr{Float64}(C_NULL)
@@ -102,9 +111,15 @@ function integrate(model::Symbol, st::SpaceTime{F}, forcings::AbstractVector{<:F
             Ef, Tgf = similar(E0), similar(Tg0)
             GC.@preserve par E0 Tg0 Ef Tgf begin
                 out = Ref(CClassicOutputs(pointer(diag), sp, rp, pointer(Ef), pointer(Tgf), pointer(flags)))
-                check(ccall(sym(:ebm_classic_run), Int32,
-                            (Ref{CGrid}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ref{COptions}, Ref{CClassicOutputs}),
-                            grid, nmem, par, forc, E0, Tg0, opt, out))
+                if multi
+                    check(ccall(sym(:ebm_classic_run_multi), Int32,
+                                (Ref{CGrid}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ref{COptions}, Ref{CMulti}, Ref{CClassicOutputs}),
+                                grid, nmem, par, forc, E0, Tg0, opt, mopt, out))
+                else
+                    check(ccall(sym(:ebm_classic_run), Int32,
+                                (Ref{CGrid}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ref{COptions}, Ref{CClassicOutputs}),
+                                grid, nmem, par, forc, E0, Tg0, opt, out))
+                end
             end
             final, stats = (E=Ef, Tg=Tgf), (;)
         else
@@ -114,10 +129,17 @@ function integrate(model::Symbol, st::SpaceTime{F}, forcings::AbstractVector{<:F
             iters, nonconv = zeros(Int64, nmem), zeros(Int64, nmem)
             GC.@preserve par s0 sf iters nonconv begin
                 out = Ref(CMizOutputs(pointer(diag), sp, rp, pointer.(sf)..., pointer(iters), pointer(nonconv), pointer(flags)))
-                check(ccall(sym(:ebm_miz_run), Int32,
-                            (Ref{CGrid}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
-                             Ptr{Float64}, Ptr{Float64}, Ref{COptions}, Ref{CMizOutputs}),
-                            grid, nmem, par, forc, s0[1], s0[2], s0[3], s0[4], s0[5], C_NULL, opt, out))
+                if multi
+                    check(ccall(sym(:ebm_miz_run_multi), Int32,
+                                (Ref{CGrid}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+                                 Ptr{Float64}, Ptr{Float64}, Ref{COptions}, Ref{CMulti}, Ref{CMizOutputs}),
+                                grid, nmem, par, forc, s0[1], s0[2], s0[3], s0[4], s0[5], C_NULL, opt, mopt, out))
+                else
+                    check(ccall(sym(:ebm_miz_run), Int32,
+                                (Ref{CGrid}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+                                 Ptr{Float64}, Ptr{Float64}, Ref{COptions}, Ref{CMizOutputs}),
+                                grid, nmem, par, forc, s0[1], s0[2], s0[3], s0[4], s0[5], C_NULL, opt, out))
+                end
             end
             verbose && any(>(0), nonconv) && @warn "Solving for T0 failed at $(sum(nonconv)) member-steps."   # miz.jl:61-63
             final = (Ei=sf[1], Ew=sf[2], h=sf[3], D=sf[4], phi=sf[5], T0=sf[6])
