@@ -150,13 +150,68 @@ def solveTi(T0, x, t, h, Tw, phi, f, par, kind, cache, Lmat, tol=1e-8):
     return T0, Ti, iters
 
 
-def miz_step(state, T0, x, t, f, dt, par, kind, cache, Lmat, tol=1e-8):
+def solveTi_trust_region(T0, x, t, h, Tw, phi, f, par, kind, cache, Lmat, abstol=1e-8, reltol=1e-6, norm="inf",
+                         radius0=None, maxit=1000):
+    """src/miz.jl:47-68 with a trust-region dogleg iteration (the algorithm family of NonlinearSolve.TrustRegion(),
+    which is not vendored: Project.toml:33 compat "4.12.0", no Manifest).  Published algorithm restated: Nocedal &
+    Wright, Numerical Optimization, Alg. 4.1 with the dogleg step (4.16) on m(p) = 1/2 |r + J p|^2, J the generalised
+    Jacobian of the piecewise-linear residual; radius shrinks by 4 when rho < 1/4, doubles when rho > 3/4 on the
+    boundary; a step is accepted when rho > 1e-4.  Stop as the reference asks (miz.jl:59): |r| <= abstol, or the
+    step is below reltol * |T0| (NonlinearSolve's relative criterion), warm start = previous T0.
+    Returns (T0, Ti, iterations, accepted_newton_steps)."""
+    hp = np.where(h == 0.0, par["hmin"], h)
+    nrm = (lambda v: float(np.max(np.abs(v)))) if norm == "inf" else (lambda v: float(np.sqrt(np.mean(v * v))))
+    res = T0eq(T0, x, t, hp, Tw, phi, f, par, kind, cache)
+    radius = radius0 if radius0 is not None else max(1.0, float(np.linalg.norm(T0)))
+    it = newton_steps = 0
+    while nrm(res) > abstol and it < maxit:
+        J = -np.diag(par["k"] / hp + par["B"]) + Lmat @ np.diag(np.where(T0 < par["Tm"], phi, 0.0))
+        g = J.T @ res
+        pN = -np.linalg.solve(J, res)
+        if np.linalg.norm(pN) <= radius:
+            p, is_newton = pN, True
+        else:
+            Jg = J @ g
+            pC = -(g @ g) / (Jg @ Jg) * g
+            is_newton = False
+            if np.linalg.norm(pC) >= radius:
+                p = -radius / np.linalg.norm(g) * g
+            else:                                   # dogleg: pC + tau (pN - pC) on the boundary
+                d = pN - pC
+                a_, b_, c_ = d @ d, 2 * (pC @ d), pC @ pC - radius**2
+                tau = (-b_ + np.sqrt(b_ * b_ - 4 * a_ * c_)) / (2 * a_)
+                p = pC + tau * d
+        new = T0eq(T0 + p, x, t, hp, Tw, phi, f, par, kind, cache)
+        pred = 0.5 * (res @ res) - 0.5 * np.sum((res + J @ p) ** 2)
+        actual = 0.5 * (res @ res) - 0.5 * (new @ new)
+        rho = actual / pred if pred > 0 else -1.0
+        if rho < 0.25:
+            radius *= 0.25
+        elif rho > 0.75 and not is_newton:
+            radius *= 2.0
+        it += 1
+        if rho > 1e-4:
+            step_small = nrm(p) <= reltol * max(nrm(T0 + p), 1e-300) and nrm(new) <= abstol * 1e2
+            T0, res = T0 + p, new
+            newton_steps += is_newton
+            if step_small:
+                break
+    Ti = jl_min(T0, par["Tm"])
+    Ti = np.where(h == 0.0, 0.0, Ti)
+    return T0, Ti, it, newton_steps
+
+
+def miz_step(state, T0, x, t, f, dt, par, kind, cache, Lmat, tol=1e-8, closure="newton"):
     """src/miz.jl:150-196.  ``state`` has Ei, Ew, h, D, phi; returns (new_vars(10), T0, iters)."""
     Ei, Ew, h, D, phi = (state[k] for k in ("Ei", "Ew", "h", "D", "phi"))
     with np.errstate(all="ignore"):
         Tw = par["Tm"] + Ew / ((1 - phi) * par["cw"])
         Tw = np.where(np.isnan(Tw), 0.0, Tw)
-        T0, Ti, iters = solveTi(T0, x, t, h, Tw, phi, f, par, kind, cache, Lmat, tol)
+        if closure == "newton":
+            T0, Ti, iters = solveTi(T0, x, t, h, Tw, phi, f, par, kind, cache, Lmat, tol)
+        else:
+            T0, Ti, iters, _ = solveTi_trust_region(T0, x, t, h, Tw, phi, f, par, kind, cache, Lmat, abstol=tol,
+                                                    norm="inf" if closure == "trust_region" else "rms")
         n = np.where(D == 0.0, 0.0, phi / (par["alpha"] * D**2))
         tb = Tbar(Ti, Tw, phi)
         L = par["A"] + par["B"] * (tb - par["Tm"])
@@ -198,23 +253,27 @@ def miz_step(state, T0, x, t, f, dt, par, kind, cache, Lmat, tol=1e-8):
     return new, T0, iters
 
 
-def miz_integrate(st, forcing, par, init, nsteps=None, tol=1e-8):
-    """integrate(:MIZ, ...) storing every step; ``nsteps`` truncates the run (tests)."""
+def miz_integrate(st, forcing, par, init, nsteps=None, tol=1e-8, closure="newton", T0=None, start_step=0):
+    """integrate(:MIZ, ...) storing every step; ``nsteps`` truncates the run (tests).  ``closure``: "newton"
+    (semi-smooth Newton, what the oracle and the kernels use), "trust_region" / "trust_region_rms" (dogleg iteration
+    with the reference's tolerances, max / rms residual norm).  ``T0`` / ``start_step``: continue from a given state."""
     kind = st.grid_kind
     cache = generic_stencil_cache(st.x) if kind == 1 else None
     Lmat = diffusion_matrix(st.x, par["D"], kind, cache)
     state = {k: np.array(init[k], dtype=float).copy() for k in ("Ei", "Ew", "h", "D", "phi")}
-    T0 = np.zeros(st.nx)
+    T0 = np.zeros(st.nx) if T0 is None else np.array(T0, dtype=float).copy()
     n = st.nt * st.dur if nsteps is None else nsteps
     names = ("T", "Ei", "Ti", "D", "n", "h", "phi", "E", "Ew", "Tw")
     out = {k: np.empty((n, st.nx)) for k in names}
     total_iters = 0
-    for tinx in range(1, n + 1):
+    for q in range(1, n + 1):
+        tinx = q + start_step
         ti = (tinx - 1) % st.nt + 1
-        new, T0, iters = miz_step(state, T0, st.x, st.t[ti - 1], forcing(st.T(tinx)), st.dt, par, kind, cache, Lmat, tol)
+        new, T0, iters = miz_step(state, T0, st.x, st.t[ti - 1], forcing(st.T(tinx)), st.dt, par, kind, cache, Lmat, tol, closure)
         total_iters += iters
         for k in names:
-            out[k][tinx - 1] = new[k]
+            out[k][q - 1] = new[k]
         state = {k: new[k] for k in ("Ei", "Ew", "h", "D", "phi")}
     out["_iters"] = total_iters
+    out["_T0"] = T0
     return out

@@ -200,3 +200,69 @@ def test_miz_is_sensitive_to_rounding_level_perturbations():
     early = max(rel_err(b["raw"][0, 9, vi], a["raw"][0, 9, vi]).max() for vi in range(10))
     late = max(rel_err(b["raw"][0, 400:, vi], a["raw"][0, 400:, vi]).max() for vi in range(10))
     assert early < 1e-6 and late > 1e-3
+
+
+# ---------------------------------------------------------------- the NonlinearSolve boundary (miz.jl:55-60)
+@pytest.mark.parametrize("closure", ["trust_region", "trust_region_rms"])
+def test_trust_region_closure_agrees_with_semismooth_newton(closure):
+    """The reference solves the surface-temperature closure with NonlinearSolve.TrustRegion() (abstol 1e-8, reltol
+    1e-6, warm start) -- a third-party dependency that is not vendored and whose version is unpinned.  The oracle and
+    the kernels use a semi-smooth Newton iteration on the same residual.  This bounds the substitution: a trust-region
+    dogleg iteration (published algorithm, Nocedal & Wright Alg. 4.1) with the reference's stop, run on the fixture
+    setup (test/runtests.jl:22-32, steps 1-20) and from year-1 / year-10 / year-30 states of the docstring run (C3),
+    gives the ten stored variables within the reference's own rtol = sqrt(eps) of the Newton run at step 10 and at
+    step 20.  (The residual is piecewise linear with a tridiagonal generalised Jacobian: whenever the Newton step
+    fits the trust radius both methods take the same step.)"""
+    rtol = 1.4901161193847656e-08
+    par = ebm.default_parameters("MIZ")
+    f = ebm.Forcing(0.0)
+
+    def compare(st, init, T0, start_step, what):
+        a = npr.miz_integrate(st, f, par, init, nsteps=20, T0=T0, start_step=start_step)
+        b = npr.miz_integrate(st, f, par, init, nsteps=20, T0=T0, start_step=start_step, closure=closure)
+        for step in (9, 19):
+            for v in ebm.MIZ_VARS:
+                x, y = np.nan_to_num(a[v][step]), np.nan_to_num(b[v][step])
+                assert np.array_equal(np.isnan(a[v][step]), np.isnan(b[v][step])), (what, v)
+                assert np.all(np.abs(x - y) <= rtol * np.maximum(np.abs(x), np.abs(y))), (what, v, step, np.abs(x - y).max())
+        return a["_iters"], b["_iters"]
+
+    st1 = ebm.SpaceTime(180, 2000, 1, "sin")
+    it_n, it_t = compare(st1, _zero(180), None, 0, "fixture setup")
+    assert it_n >= 20 and it_t >= 20
+    for years in (1, 10, 30):
+        st = ebm.SpaceTime(180, 2000, years, "sin")
+        o = oracle_miz(st, [f], [par], [_zero(180)])
+        init = ebm.Collection(**{k: o[k][0] for k in ("Ei", "Ew", "h", "D", "phi")})
+        compare(st, init, o["T0"][0], years * 2000, f"C3 after {years} years")
+
+
+def test_c5_blow_up_members_blow_up_in_the_independent_restatement_too():
+    """Part of the C5 sweep (D, B, ai, k, m1 over 16^5 values) has no finite solution in the reference
+    ALGORITHM: lateral melt too weak (m1 below its default) lets the ice concentration reach phi = 1 next to warm water
+    and water_temp (miz.jl:30) divides by 1 - phi = 0.  The C oracle and the independent NumPy restatement (different
+    code, dense solves) agree on which members blow up and on the year; a neighbouring member with default m1 stays
+    finite in both.  bench.py reports such members (`nan_members`) and the throughput over finite members."""
+    import bench
+    N = 16 ** 5
+    # (member index in the 16^5 grid, blows up within 5 years?) -- found with the oracle on a 512-member sample
+    cases = [(20776, True), (196911, True)]
+    st5 = ebm.SpaceTime(180, 2000, 5, "sin")
+    idx = np.array([c[0] for c in cases] + [0])
+    _, rows, forc, init = bench.miz_workload(ebm, N, idx, 5)
+    rows[-1] = [ebm.default_parameters("MIZ")[k] for k in ebm.MIZ_PAR_ORDER]        # default parameters: stable
+    o = oracle.miz_run(st5.x, st5.t, 5, st5.winter.inx, st5.summer.inx, st5.grid_kind, rows, forc, *init)
+    finite = np.isfinite(o["Ei"]).all(axis=1) & np.isfinite(o["Ew"]).all(axis=1)
+    assert list(finite) == [False, False, True]
+    order = list(ebm.MIZ_PAR_ORDER)
+    for k, (m, blows) in enumerate(cases[:1] + [(None, False)]):
+        par = ebm.Collection(dict(zip(order, rows[k if m is not None else -1])))
+        blew = False
+        try:
+            with np.errstate(all="ignore"):
+                r = npr.miz_integrate(st5, ebm.Forcing(0.0), par, _zero(180), nsteps=(5 if blows else 1) * 2000)
+            blew = not (np.isfinite(r["Ei"][-1]).all() and np.isfinite(r["Ew"][-1]).all())
+        except (RuntimeError, np.linalg.LinAlgError):
+            blew = True                                   # closure residual is NaN: no convergence, or a singular Jacobian
+        assert blew == blows, (m, blows)
+    assert rows[0][order.index("m1")] > 0 and rows[1][order.index("ai")] < 0.4
