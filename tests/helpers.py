@@ -90,3 +90,12 @@ def assert_close(a, ref, tol, what="", flag=None, flag_tol=1e-6, max_flag_frac=1
     if flag.any() and err[flag].max() >= flag_tol:
         raise AssertionError(f"{what}: flagged-cell err {err[flag].max():.3e} >= {flag_tol:.1e}")
     return int(flag.sum())
+
+
+def classic_branch_flags(raw, raw_ref, thresh=1e-6):
+    """SURVEY 8c "flagged cells" for classic raw output [..., nraw, 3 (E, T, h), nx]: samples of a cell-step whose
+    oracle enthalpy sits within `thresh` of the ice/water branch threshold E = 0, or whose ice mask differs between
+    the kernel and the oracle.  Such samples are counted, reported and held to the looser flag tolerance."""
+    E, Er = raw[..., 0, :], raw_ref[..., 0, :]
+    f = (np.abs(Er) < thresh) | ((E < 0) != (Er < 0))
+    return np.broadcast_to(f[..., None, :], raw.shape).copy()

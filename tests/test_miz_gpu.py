@@ -144,7 +144,8 @@ def test_strict_kernel_bitwise_thirty_years():
 
 def test_fast_kernel_thirty_years_climatology():
     """C3 with the fast kernel: Solutions layout, and the year-30 climate within the model's own sensitivity
-    envelope (a 1e-13 perturbation of the oracle moves these diagnostics by ~2e-3)."""
+    envelope, measured in the test with a perturbed oracle run (see also
+    test_fast_kernel_divergence_is_bounded_by_the_models_own_sensitivity)."""
     st = ebm.SpaceTime(180, 2000, 30, "sin")
     par, f, init = _par(), ebm.Forcing(0.0), _zero(180)
     o = oracle_miz(st, [f], [par], [init], seasonal=True)
@@ -153,7 +154,16 @@ def test_fast_kernel_thirty_years_climatology():
     assert abs(sols.ts[0] - 29.00025) < 1e-12 and len(sols.ts) == 2000 and sols.raw.E.shape == (2000, 180)
     od = oracle_diag_miz(o["seasonal"], st.x)
     d = np.abs(r.diag[0, 29] - od[0, 29])
-    assert d[:, 0].max() < 0.05 and d[:, 1].max() < 0.1 and d[:, 2].max() < 0.02 and d[:, 3].max() < 0.03, d
+    # derived envelope: the oracle's own response to a rounding-level perturbation (1e-14 added to the first step's
+    # water enthalpy) -- the fast kernel may differ from the oracle by at most 10x that, diagnostic by diagnostic
+    pin = _zero(180)
+    pin.Ew = pin.Ew + 1e-14
+    op = oracle_miz(st, [f], [par], [pin], seasonal=True)
+    env = np.abs(oracle_diag_miz(op["seasonal"], st.x)[0, 29] - od[0, 29])
+    floor = np.array([1e-6, 1e-6, 1e-6, 0.0])[None, :]            # ice edge is quantised to the grid: no floor needed
+    dx = float(np.diff(st.x).max())
+    env[:, 3] = np.maximum(env[:, 3], dx)                          # ... but it moves by whole cells
+    assert (d <= 10.0 * np.maximum(env, floor)).all(), (d, env)
     ice_cells = int((sols.raw.phi[-1] > 0).sum())
     assert 30 <= ice_cells <= 90                       # SURVEY Appendix D probe: ice cells 175 -> 57
     assert r.nonconv[0] == 0 and r.flags[0] == 0
@@ -259,7 +269,12 @@ def test_state_invariants_large_ensemble():
     idx = list(range(0, nmem, 512))
     o = oracle_miz(st, [forcings[i] for i in idx], [pars[i] for i in idx], [_zero(nx)] * len(idx), seasonal=True)
     od = oracle_diag_miz(o["seasonal"], st.x)
-    assert np.abs(r.diag[idx, 0, 2, 0] - od[:, 0, 2, 0]).max() < 0.5      # annual-mean hemispheric T
+    # envelope derived from the oracle's own sensitivity (perturbed run), member by member
+    pin = _zero(nx)
+    pin.Ew = pin.Ew + 1e-14
+    op = oracle_miz(st, [forcings[i] for i in idx], [pars[i] for i in idx], [pin] * len(idx), seasonal=True)
+    env = np.abs(oracle_diag_miz(op["seasonal"], st.x)[:, 0, 2, 0] - od[:, 0, 2, 0])
+    assert (np.abs(r.diag[idx, 0, 2, 0] - od[:, 0, 2, 0]) <= 10.0 * np.maximum(env, 1e-6)).all()      # annual-mean hemispheric T
 
 
 def test_c5_members_five_years():
@@ -291,7 +306,12 @@ def test_c5_members_five_years():
     assert (f["phi"][ok] >= 0).all() and (f["phi"][ok] <= 1).all() and (f["h"][ok] >= 0).all()
     assert (f["Ei"][ok] <= 0).all() and (f["Ew"][ok] >= 0).all() and r.nonconv[ok].max() == 0
     od = oracle_diag_miz(o["seasonal"], st.x)
-    assert np.abs(r.diag[ok, -1, 2, 0] - od[ok, -1, 2, 0]).max() < 0.5
+    pin = _zero(180)
+    pin.Ew = pin.Ew + 1e-14
+    op = oracle_miz(st, forcings, pars, [pin] * nsub, seasonal=True)
+    okp = ok & np.isfinite(op["Ei"]).all(axis=1)
+    env = np.abs(oracle_diag_miz(op["seasonal"], st.x)[:, -1, 2, 0] - od[:, -1, 2, 0])
+    assert (np.abs(r.diag[okp, -1, 2, 0] - od[okp, -1, 2, 0]) <= 10.0 * np.maximum(env[okp], 1e-6)).all()
 
 
 def test_fast_kernel_divergence_is_bounded_by_the_models_own_sensitivity(capsys):
