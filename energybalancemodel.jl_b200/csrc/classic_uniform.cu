@@ -128,7 +128,13 @@ struct Ctx {
   __device__ __forceinline__ int cidx(int i) const { return WARPM ? (i * (WB * MW) + (int)threadIdx.x) : ((j0 + i) * MW + mi); }
   bool active, sel, cta_fields;
   bool solver;   // this warp solves the CTA's interface systems (the warp that owns band pair 1: never the polar pair)
-  long long m, mo, msel;   // slot in this launch, original member index (output rows), index among field-output members
+  // original member index of this thread's member (output rows, field selection): recomputed where it is needed (the
+  // three sampling steps of a year) instead of being kept in registers through the hot loop
+  __device__ __forceinline__ long long member_orig(const ClassicKArgs& a) const {
+    long long m = ((long long)(blockIdx.x + (unsigned)a.block0)) * MW + mi;
+    if (m >= a.nmem) m = a.nmem - 1;
+    return a.orig != nullptr ? a.orig[m] : m;
+  }
   // state
   double E[K], Tg[K], accT;
   RowStore<K, QS_SMEM> rs;
@@ -152,6 +158,7 @@ struct Ctx {
       if (rawstep && j < nx) {
         const long long nraw = a.lastonly ? (long long)nt : (long long)nt * a.dur;
         const long long rawidx = a.lastonly ? (ti - 1) : ((long long)year * nt + ti - 1);
+        const long long msel = member_orig(a) / a.field_stride;
         double* o = a.raw + ((msel * nraw + rawidx) * 3) * (long long)nx + j;
         o[0] = En; o[nx] = T; o[2 * nx] = -Eneg * inv_Lf;          // h = -E/Lf*(E<0)  (classic.jl:65)
       }
@@ -165,6 +172,7 @@ struct Ctx {
         dgE = fma(wj, vE, dgE);
         if (vE < 0.0 && j < nx) { dgA += wj; dgX = fmin(dgX, phys[j].S1x); }
         if (sel && a.seasonal != nullptr && j < nx) {
+          const long long msel = member_orig(a) / a.field_stride;
           double* o = a.seasonal + ((((msel * a.dur + year) * 3 + season) * 3) * (long long)nx) + j;
           o[0] = vE; o[nx] = vT; o[2 * nx] = -vN * inv_Lf;
         }
@@ -450,7 +458,7 @@ struct Ctx {
           dgA += __shfl_xor_sync(kFull, dgA, o); dgX = fmin(dgX, __shfl_xor_sync(kFull, dgX, o));
         }
         if (band == 0 && a.diag != nullptr && active) {
-          double* o = a.diag + ((mo * a.dur + year) * 3 + season) * 4;
+          double* o = a.diag + ((member_orig(a) * a.dur + year) * 3 + season) * 4;
           o[0] = dgT; o[1] = dgE; o[2] = kTwoPi * dgA; o[3] = (dgX > 1.5) ? 1.0 : dgX;
         }
       }
@@ -515,7 +523,7 @@ struct Ctx {
           t1 += r4[1 * MW]; t2 += r4[2 * MW]; t3 = fmin(t3, r4[3 * MW]);
           t0 += r4[0 * MW];
         }
-        double* o = a.diag + ((mo * a.dur + year) * 3 + season) * 4;
+        double* o = a.diag + ((member_orig(a) * a.dur + year) * 3 + season) * 4;
         o[0] = t0; o[1] = t1; o[2] = kTwoPi * t2; o[3] = (t3 > 1.5) ? 1.0 : t3;
       }
     }
@@ -569,11 +577,11 @@ __global__ void __maxnreg__(MAXR) classic_uniform_kernel(const ClassicKArgs a) {
   // which band pair a warp owns rotates with the CTA index: in a partially ice-covered member only the polar bands
   // take the expensive path, and without the rotation every resident CTA puts that warp on the same SM sub-partition
   constexpr int NWARP = WB * MW / 32;
-  const long long bid = (long long)blockIdx.x + a.block0;   // 16-member group of this CTA
+  const unsigned bid = blockIdx.x + (unsigned)a.block0;   // 16-member group of this CTA
   const int wrot = (a.dbg & 4) ? warp : (int)((warp + bid) % NWARP);
   const int band = WARPM ? (lane / (32 / WB)) : (wrot * BPW + lane / MW);
   const long long nmem = a.nmem;
-  const long long m_first = bid * MW;
+  const long long m_first = (long long)bid * MW;
   const long long m_raw = m_first + mi;
   const bool active = m_raw < nmem;
   const long long m = active ? m_raw : nmem - 1;
@@ -665,10 +673,7 @@ __global__ void __maxnreg__(MAXR) classic_uniform_kernel(const ClassicKArgs a) {
   cx.solver = WARPM ? false : ((a.dbg & 8) ? warp == 0 : (wrot == (NWARP > 1 ? 1 : 0)));
   cx.active = active;
   const long long mo = a.orig != nullptr ? a.orig[m] : m;   // ebm_classic_device_args_t.member_index
-  cx.mo = mo;
   cx.sel = active && a.field_stride > 0 && (mo % a.field_stride) == 0;
-  cx.msel = cx.sel ? mo / a.field_stride : 0;
-  cx.m = m;
   cx.cta_fields = __syncthreads_or(cx.sel && (a.seasonal != nullptr)) != 0;
   cx.accT = 0.0;
 #pragma unroll
