@@ -307,15 +307,17 @@ extern "C" int32_t ebm_classic_run_device(const ebm_grid_t* grid, const ebm_clas
     const long long waves = slots > 0 ? (blocks + slots - 1) / slots : 0;
     if (slots > 0 && blocks > slots && blocks <= 12 * slots && grid->dur >= 8 &&
         (double)(waves * slots) > 1.08 * (double)blocks) {
-      constexpr int S = 8;
-      const int chunk = std::min(ypl, std::max(1, grid->dur / 16));
+      constexpr int SMAX = 32;
+      static const int S = std::min(SMAX, std::max(1, getenv("EBM_WB_STREAMS") ? atoi(getenv("EBM_WB_STREAMS")) : 8));
+      static const int nchunk = std::max(1, getenv("EBM_WB_CHUNKS") ? atoi(getenv("EBM_WB_CHUNKS")) : 16);
+      const int chunk = std::min(ypl, std::max(1, grid->dur / nchunk));
       a.uniform_split = 1;
       cudaEvent_t fork;
       EBM_CUDA_TRY(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
       EBM_CUDA_TRY(cudaEventRecord(fork, stream));
       int rc = EBM_OK;
-      cudaStream_t aux[S];
-      cudaEvent_t done[S];
+      cudaStream_t aux[SMAX];
+      cudaEvent_t done[SMAX];
       int made = 0;
       for (; made < S && rc == EBM_OK; ++made) {
         if (cudaStreamCreateWithFlags(&aux[made], cudaStreamNonBlocking) != cudaSuccess ||
