@@ -4,7 +4,7 @@
 // no FMA contraction (every op is an explicit __d*_rn intrinsic), masks as selects, and the
 // tridiagonal solve in the LU order a dense `\` without row swaps reduces to.  State and scratch
 // live in global memory; this kernel exists for parity debugging (ebm_options_t.strict) and for the
-// one-step entry point ebm_classic_step -- it is not the fast path (classic_bands.cu is).
+// one-step entry point ebm_classic_step -- it is not the fast path (classic_uniform.cu is).
 #include "ebm_internal.cuh"
 
 namespace {

@@ -1,9 +1,8 @@
 // miz_literal.cuh -- the marginal-ice-zone (MIZ) ensemble step kernel written in the reference's operation order.
-// Included by miz_strict.cu with EBM_MIZ_STRICT=1 and compiled with -fmad=false: literal arithmetic, IEEE
-// division, serial Thomas solve in the oracle's order -- bit-identical to the oracle; used for parity debugging
-// (ebm_options_t.strict) and by the one-step entry point ebm_miz_step.  With EBM_MIZ_STRICT=0 the same source is
-// the first, unoptimised fast flavour (kept compilable as a reference point); the production fast kernel, same
-// mapping with the arithmetic restructured for the FP64 pipe, is miz_kernel.cu.
+// Included by miz_strict.cu and compiled with -fmad=false: literal arithmetic, IEEE division, serial Thomas solve in
+// the oracle's order -- bit-identical to the oracle; used for parity debugging (ebm_options_t.strict) and by the
+// one-step entry point ebm_miz_step.  The production fast kernel, same mapping with the arithmetic restructured for
+// the FP64 pipe, is miz_kernel.cu.
 //
 // Replaces, for a whole ensemble and many years per launch, the reference's
 //   integrate loop            src/infrastructure.jl:630-634
@@ -30,15 +29,12 @@
 
 #include "ebm_internal.cuh"
 
-#ifndef EBM_MIZ_STRICT
-#define EBM_MIZ_STRICT 0
-#endif
 
 namespace {
 
 constexpr double kPi = 3.141592653589793;   // Float64(pi)
 constexpr unsigned kFull = 0xffffffffu;
-constexpr int kWarpsPerCta = EBM_MIZ_STRICT ? 1 : 4;
+constexpr int kWarpsPerCta = 1;
 
 // Julia min(a, b): NaN-propagating
 __device__ __forceinline__ double jl_min(double a, double b) {
@@ -73,11 +69,9 @@ struct MizTabs {
   double x[K * 32], x2[K * 32], wts[K * 32];
   // fast flavour: diffusion_j = D*(cu_j*(T[j+1]-T[j]) - cl_j*(T[j]-T[j-1]))
   double cu[K * 32], cl[K * 32];
-#if EBM_MIZ_STRICT
   // literal stencils: generic (mxxph, mxxmh, phmmh, diffx[j+1], diffx[j]) / identity (lam_hi, lam_lo)
   double mxxph[K * 32], mxxmh[K * 32], phmmh[K * 32], dxp[K * 32], dxm[K * 32];
   double scratch[6][K * 32];   // serial Thomas: jl, jd, ju, rhs, w, y
-#endif
 };
 
 template <int K>
@@ -102,7 +96,6 @@ __device__ __forceinline__ void miz_diffusion(const MizTabs<K>& tb_, const MizPa
     const int s = i * 32 + lane;
     const double tm = (i == 0) ? left : tb[i - 1];
     const double tp = (i == K - 1) ? right : tb[i + 1];
-#if EBM_MIZ_STRICT
     const int j = lane * K + i;
     if (kind == 1) {
       const double dTp = (j < nx - 1) ? tp - tb[i] : 0.0;       // diffT[i]   (:522-523)
@@ -119,12 +112,6 @@ __device__ __forceinline__ void miz_diffusion(const MizTabs<K>& tb_, const MizPa
       if (j < nx - 1) acc += (p.D * lp) * tp;
       out[i] = acc;
     }
-#else
-    (void)kind; (void)nx;
-    const double cu = tb_.cu[s], cl = tb_.cl[s];
-    // a zero coefficient must silence a garbage neighbour (lane 0 / lane 31 shuffles return own values: finite)
-    out[i] = p.D * (cu * (tp - tb[i]) - cl * (tb[i] - tm));
-#endif
   }
 }
 
@@ -133,7 +120,6 @@ __device__ __forceinline__ void miz_diffusion(const MizTabs<K>& tb_, const MizPa
 template <int K>
 __device__ __forceinline__ void miz_tridiag(MizTabs<K>& tabs, int warp, int nx, int lane, const double (&jl)[K],
                                             const double (&jd)[K], const double (&ju)[K], double (&rhs)[K]) {
-#if EBM_MIZ_STRICT
   (void)warp;
   // literal Thomas in the oracle's order (one lane), through shared memory
   double* sl = tabs.scratch[0]; double* sd = tabs.scratch[1]; double* su = tabs.scratch[2];
@@ -162,68 +148,6 @@ __device__ __forceinline__ void miz_tridiag(MizTabs<K>& tabs, int warp, int nx, 
     rhs[i] = (j < nx) ? sr[j] : 0.0;
   }
   __syncwarp();
-#else
-  (void)tabs; (void)warp; (void)nx;
-  // local forward elimination:  x_i + q_i x_{i+1} + s_i xL = y_i   (xL = last unknown of the previous lane)
-  double q[K], s[K];
-  {
-    double qp = 0.0, yp = 0.0, sp = 0.0;
-#pragma unroll
-    for (int i = 0; i < K; ++i) {
-      const double w = (i == 0) ? jd[i] : fma(-jl[i], qp, jd[i]);
-      const double iw = 1.0 / w;
-      q[i] = ju[i] * iw;
-      const double yi = (i == 0) ? rhs[i] * iw : fma(-jl[i], yp, rhs[i]) * iw;
-      const double si = (i == 0) ? jl[i] * iw : -(jl[i] * sp) * iw;
-      s[i] = si; rhs[i] = yi;
-      qp = q[i]; yp = yi; sp = si;
-    }
-  }
-  // reduce row 0 to  x_0 = al - be*xL - ga*z   (z = my last unknown)
-  double al = rhs[K - 2], be = s[K - 2], ga = q[K - 2];
-#pragma unroll
-  for (int i = K - 3; i >= 0; --i) {
-    al = fma(-q[i], al, rhs[i]);
-    be = fma(-q[i], be, s[i]);
-    ga = -q[i] * ga;
-  }
-  // interface row of this lane:  A z_{l-1} + B z_l + C z_{l+1} = R, using the next lane's (al, be, ga)
-  const double nal = shfl_dn1(al), nbe = shfl_dn1(be), nga = shfl_dn1(ga);
-  const double ql = (lane == 31) ? 0.0 : q[K - 1];
-  double A = (lane == 0) ? 0.0 : s[K - 1];
-  double B = fma(-ql, nbe, 1.0);
-  double C = -ql * nga;
-  double R = fma(-ql, nal, rhs[K - 1]);
-  {
-    const double ib = 1.0 / B;
-    A *= ib; C *= ib; R *= ib;
-  }
-  // parallel cyclic reduction, rows kept normalised (B = 1); out-of-range neighbours are identity rows
-#pragma unroll
-  for (int st = 1; st < 32; st <<= 1) {
-    const bool hu = lane >= st, hd = lane + st < 32;
-    const double Au = __shfl_up_sync(kFull, A, st), Cu = __shfl_up_sync(kFull, C, st), Ru = __shfl_up_sync(kFull, R, st);
-    const double Ad = __shfl_down_sync(kFull, A, st), Cd = __shfl_down_sync(kFull, C, st), Rd = __shfl_down_sync(kFull, R, st);
-    const double a_ = hu ? A : 0.0, c_ = hd ? C : 0.0;
-    const double Bn = fma(-a_, Cu, fma(-c_, Ad, 1.0));
-    const double ib = 1.0 / Bn;
-    const double Rn = fma(-a_, Ru, fma(-c_, Rd, R));
-    A = -(a_ * Au) * ib;
-    C = -(c_ * Cd) * ib;
-    R = Rn * ib;
-  }
-  // back substitution with the true neighbours
-  const double z = R;
-  const double zup = shfl_up1(z);              // every lane must execute the shuffle (full mask)
-  const double xL = (lane == 0) ? 0.0 : zup;
-  double xn = z;
-  rhs[K - 1] = z;
-#pragma unroll
-  for (int i = K - 2; i >= 0; --i) {
-    xn = fma(-q[i], xn, fma(-s[i], xL, rhs[i]));
-    rhs[i] = xn;
-  }
-#endif
 }
 
 // ---- closure: solveTi (src/miz.jl:47-68) ----------------------------------------------------------------------------
@@ -285,7 +209,6 @@ __device__ __forceinline__ int miz_solveTi(MizTabs<K>& tabs, const MizPar& p, in
       const double gm = (i == 0) ? gleft : g[i - 1];
       const double gp = (i == K - 1) ? gright : g[i + 1];
       double lo, up, di;
-#if EBM_MIZ_STRICT
       if (kind == 1) {   // oracle miz_diff_coeffs
         up = (j < nx - 1) ? p.D * tabs.mxxph[s] / tabs.dxp[s] / tabs.phmmh[s] : 0.0;
         lo = (j > 0) ? p.D * tabs.mxxmh[s] / tabs.dxm[s] / tabs.phmmh[s] : 0.0;
@@ -296,9 +219,6 @@ __device__ __forceinline__ int miz_solveTi(MizTabs<K>& tabs, const MizPar& p, in
         const double l3 = -l1 - l2;
         lo = (j > 0) ? p.D * lm : 0.0; up = (j < nx - 1) ? p.D * lp : 0.0; di = p.D * (-l3);
       }
-#else
-      lo = p.D * tabs.cl[s]; up = p.D * tabs.cu[s]; di = -(lo + up);
-#endif
       jd[i] = -(p.k / hp[i] + p.B) + di * g[i];
       jl[i] = (j > 0 && j < nx) ? lo * gm : 0.0;
       ju[i] = (j < nx - 1) ? up * gp : 0.0;
@@ -379,11 +299,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) miz_warp_kernel(const MizKA
       }
     }
     tabs.cu[s] = cu; tabs.cl[s] = cl;
-#if EBM_MIZ_STRICT
     tabs.mxxph[s] = v ? a.g.mxxph[j] : 0.0; tabs.mxxmh[s] = v ? a.g.mxxmh[j] : 0.0;
     tabs.phmmh[s] = v ? a.g.phmmh[j] : 1.0;
     tabs.dxp[s] = v ? a.g.diffx[j + 1] : 1.0; tabs.dxm[s] = v ? a.g.diffx[j] : 1.0;
-#endif
   }
   __syncthreads();
 
