@@ -193,7 +193,7 @@ def cpu_run(workload, nmem_total, years, sample_members, threads, solver=0):
     return len(idx) * years / dt, dt, f"{len(idx)} members (stride {stride}, even and odd alternating) x {years} years, seasonal sampling on"
 
 
-def cpu_baseline(workload, nmem_total, years, threads, sample_members=0, target_s=12.0):
+def cpu_baseline(workload, nmem_total, years, threads, sample_members=0, target_s=20.0):
     """B-cpu of BASELINE.md 3: the oracle on all host cores, on a sample sized for >= ~10 s of CPU work (a short
     probe fixes the rate first), plus -- classic only -- B-ref-proxy (dense LU of the nx x nx matrix every step, as
     the reference's `\\` does, one thread) and B-pub (the reference's one published figure)."""

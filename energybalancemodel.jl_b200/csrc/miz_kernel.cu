@@ -72,8 +72,22 @@ __device__ __forceinline__ double keep(double v) {
   return v;
 }
 __device__ __forceinline__ double sel(bool c, double a, double b) { return c ? keep(a) : keep(b); }
+#ifdef EBM_MIZ_SELP
 __device__ __forceinline__ double sel0(bool c, double b) { return c ? 0.0 : keep(b); }   // c ? 0 : b
 __device__ __forceinline__ double sel1(bool c, double b) { return c ? 1.0 : keep(b); }   // c ? 1 : b
+#else
+// c ? 0 : b and c ? 1 : b as bit masks on the two words (2 LOP3 each; the mask of a condition is shared by all its
+// uses): ptxas lowers a select against an immediate 0.0 / 1.0 to "materialise the constant + two predicated moves",
+// 3-4 instructions per select and a third of this kernel's instruction count (profiles/r2_miz_fast_ncu.txt)
+__device__ __forceinline__ double sel0(bool c, double b) {
+  const int m = c ? 0 : -1;
+  return __hiloint2double(__double2hiint(b) & m, __double2loint(b) & m);
+}
+__device__ __forceinline__ double sel1(bool c, double b) {
+  const int m = c ? 0 : -1;
+  return __hiloint2double((__double2hiint(b) & m) | (0x3ff00000 & ~m), __double2loint(b) & m);
+}
+#endif
 // zero / sign tests on the integer pipe (the FP64 pipe is the bottleneck); +0 and -0 are both zero
 __device__ __forceinline__ bool is_zero(double v) { return ((__double2hiint(v) << 1) | __double2loint(v)) == 0; }
 // x / y with y an ordinary non-zero number (no denormal / huge denominators: DESIGN.md 4.3)
