@@ -36,7 +36,7 @@ class Grid(C.Structure):
 class Options(C.Structure):
     _fields_ = [("device", C.c_int32), ("lastonly", C.c_int32), ("field_stride", C.c_int32), ("strict", C.c_int32),
                 ("years_per_launch", C.c_int32), ("newton_maxit", C.c_int32), ("newton_tol", C.c_double),
-                ("step_limit", C.c_int32), ("start_year", C.c_int32)]
+                ("step_limit", C.c_int32), ("start_year", C.c_int32), ("classic_stencil", C.c_int32)]
 
 
 class ClassicOutputs(C.Structure):
@@ -144,6 +144,6 @@ def make_multi(ndevices=0, devices=None, diag_device=-1, packet=0) -> Multi:
 
 
 def make_options(device=-1, lastonly=True, field_stride=0, strict=False, years_per_launch=0, newton_maxit=0,
-                 newton_tol=0.0, step_limit=0, start_year=0) -> Options:
+                 newton_tol=0.0, step_limit=0, start_year=0, classic_stencil=0) -> Options:
     return Options(device, int(lastonly), field_stride, int(strict), years_per_launch, newton_maxit, newton_tol,
-                   step_limit, start_year)
+                   step_limit, start_year, int(classic_stencil))

@@ -78,9 +78,10 @@ __device__ void classic_step_literal(const EbmGridTables& g, const double* p, lo
   // tridiagonal solve, LU order: l = a/w; w' = d - l*c; y' = r - l*y; x = (y - c*x')/w
   w[0] = dg[0];
   for (int j = 1; j < nx; ++j) {
-    const double off = -Lit::div(Lit::mul(s.dtD, g.lam_lo[j]), cg);  // kappa off-diagonal between j-1 and j
+    const double off = -Lit::div(Lit::mul(s.dtD, g.lam_lo[j]), cg);      // kappa sub-diagonal: row j, column j-1
+    const double sup = -Lit::div(Lit::mul(s.dtD, g.lam_hi[j - 1]), cg);  // super-diagonal of row j-1 (the same value with get_diffop)
     const double l = Lit::div(off, w[(j - 1) * stride]);
-    w[j * stride] = Lit::sub(dg[j * stride], Lit::mul(l, off));
+    w[j * stride] = Lit::sub(dg[j * stride], Lit::mul(l, sup));
     y[j * stride] = Lit::sub(y[j * stride], Lit::mul(l, y[(j - 1) * stride]));
   }
   double xn = Lit::div(y[(nx - 1) * stride], w[(nx - 1) * stride]);

@@ -81,12 +81,13 @@ int get_tables(const ebm_grid_t* g, EbmGridTables* out, cudaStream_t stream) {
     }
   }
   const int nx = g->nx, nt = g->nt;
-  // layout: x, x2, lam_lo, lam_hi, wts [nx each]; ctab [nt+1]; diffx [nx+1]; mxxph, mxxmh, phmmh [nx each]
-  const size_t n = (size_t)5 * nx + (nt + 1) + (nx + 1) + (size_t)3 * nx;
+  // layout: x, x2, lam_lo, lam_hi, wts [nx each]; ctab [nt+1]; diffx [nx+1]; mxxph, mxxmh, phmmh, glam_lo, glam_hi [nx each]
+  const size_t n = (size_t)5 * nx + (nt + 1) + (nx + 1) + (size_t)5 * nx;
   std::vector<double> hbuf(n, 0.0);
   double* x = hbuf.data(); double* x2 = x + nx; double* lam_lo = x2 + nx; double* lam_hi = lam_lo + nx;
   double* wts = lam_hi + nx; double* ctab = wts + nx; double* diffx = ctab + nt + 1;
   double* mxxph = diffx + nx + 1; double* mxxmh = mxxph + nx; double* phmmh = mxxmh + nx;
+  double* glo = phmmh + nx; double* ghi = glo + nx;
   const double dx = 1.0 / nx;
   for (int j = 0; j < nx; ++j) { x[j] = g->x[j]; x2[j] = g->x[j] * g->x[j]; }
   // get_diffop (src/infrastructure.jl:482-484): xb = dx:dx:1-dx (== j/nx), lambda = (1 - xb^2)/dx^2
@@ -115,6 +116,8 @@ int get_tables(const ebm_grid_t* g, EbmGridTables* out, cudaStream_t stream) {
       const int i = j + 1;
       const double xxph = (xe[i + 1] + xe[i]) / 2.0, xxmh = (xe[i] + xe[i - 1]) / 2.0;
       mxxph[j] = 1.0 - xxph * xxph; mxxmh[j] = 1.0 - xxmh * xxmh; phmmh[j] = xxph - xxmh;
+      glo[j] = j > 0 ? mxxmh[j] / (diffx[j] * phmmh[j]) : 0.0;            // zero flux at both ends (:520-521)
+      ghi[j] = j < nx - 1 ? mxxph[j] / (diffx[j + 1] * phmmh[j]) : 0.0;
     }
   }
   double* dbuf = nullptr;
@@ -127,6 +130,7 @@ int get_tables(const ebm_grid_t* g, EbmGridTables* out, cudaStream_t stream) {
   e.tabs.x = dbuf; e.tabs.x2 = dbuf + nx; e.tabs.lam_lo = dbuf + 2 * nx; e.tabs.lam_hi = dbuf + 3 * nx;
   e.tabs.wts = dbuf + 4 * nx; e.tabs.ctab = dbuf + 5 * nx; e.tabs.diffx = e.tabs.ctab + nt + 1;
   e.tabs.mxxph = e.tabs.diffx + nx + 1; e.tabs.mxxmh = e.tabs.mxxph + nx; e.tabs.phmmh = e.tabs.mxxmh + nx;
+  e.tabs.glam_lo = e.tabs.phmmh + nx; e.tabs.glam_hi = e.tabs.glam_lo + nx;
   // bounded: the least recently used entry goes when the cache is full.  Its tables may still be read by kernels in
   // flight on other streams, so the block is released only after the device has drained.
   if (g_cache.size() >= kMaxGridCache) {
@@ -286,6 +290,12 @@ extern "C" int32_t ebm_classic_run_device(const ebm_grid_t* grid, const ebm_clas
   ClassicKArgs a;
   memset(&a, 0, sizeof(a));
   EBM_TRY(get_tables(grid, &a.g, stream));
+  if (opt.classic_stencil == 1) {   // classic on non-uniform grids: the generic flux-form stencil in kappa
+    a.g.lam_lo = a.g.glam_lo; a.g.lam_hi = a.g.glam_hi;
+  } else if (opt.classic_stencil != 0) {
+    ebm_set_error("classic_stencil must be 0 (get_diffop, as the reference) or 1 (generic flux-form stencil)");
+    return EBM_ERR_INVALID;
+  }
   a.nx = grid->nx; a.nt = grid->nt; a.dur = grid->dur; a.nmem = args->nmem;
   a.winter_inx = grid->winter_inx; a.summer_inx = grid->summer_inx;
   a.lastonly = opt.lastonly; a.field_stride = opt.field_stride;
@@ -356,7 +366,7 @@ extern "C" int32_t ebm_classic_run_device(const ebm_grid_t* grid, const ebm_clas
       // nx <= 104: the table-driven kernel takes the 32-member groups whose table-building parameters agree, its
       // per-member-coefficient instance the others; larger grids (or EBM_CLASSIC_VARIANT < 0): the band kernel
       a.uniform_split = (a.nx <= ebm_classic_uniform_max_nx() && variant >= 0) ? 1 : 0;
-      if (a.uniform_split && variant >= 20) {
+      if (a.uniform_split && variant >= 20 && opt.classic_stencil == 0) {
         // experimental one-barrier kernel (classic_fused.cu; EBM_CLASSIC_VARIANT >= 20): measured slower than the
         // two-barrier kernel in every regime, kept for the record
         EBM_TRY(ebm_launch_classic_fused(a, variant, stream));

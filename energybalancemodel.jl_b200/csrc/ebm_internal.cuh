@@ -47,6 +47,9 @@ struct EbmGridTables {
   const double* mxxph;   // [nx]
   const double* mxxmh;   // [nx]
   const double* phmmh;   // [nx]
+  // the same stencil as matrix coefficients (classic on non-uniform grids, ebm_options_t.classic_stencil)
+  const double* glam_lo; // [nx]      mxxmh / (diffx[j] * phmmh),   0 at j = 0
+  const double* glam_hi; // [nx]      mxxph / (diffx[j+1] * phmmh), 0 at j = nx-1
 };
 
 // ----------------------------------------------------------------------------- kernel argument blocks

@@ -106,7 +106,7 @@ def integrate_arrays(model, st: SpaceTime, forc, par, state, *, lastonly: bool =
                      want_diag: bool = True, want_seasonal: bool | None = None, want_raw: bool | None = None,
                      device: int = -1, strict: bool = False, years_per_launch: int = 0,
                      newton_tol: float = 0.0, newton_maxit: int = 0, step_limit: int = 0,
-                     start_year: int = 0, devices=None, packet: int = 0) -> EnsembleResult:
+                     start_year: int = 0, devices=None, packet: int = 0, classic_stencil: int = 0) -> EnsembleResult:
     """Array form for large ensembles (no per-member Python objects): ``forc[nmem, 10]`` (``Forcing.row()`` layout),
     ``par[nmem, 15 | 22]`` in ``CLASSIC_PAR_ORDER`` / ``MIZ_PAR_ORDER``, ``state`` a dict of ``[nmem, nx]`` arrays
     (classic ``E, Tg``; MIZ ``Ei, Ew, h, D, phi`` and optionally the closure warm start ``T0``) -- exactly the buffers
@@ -114,7 +114,11 @@ def integrate_arrays(model, st: SpaceTime, forc, par, state, *, lastonly: bool =
 
     ``devices``: a list of CUDA ordinals (or an int n = the first n devices, 0 = all) runs the ensemble on several
     GPUs through ``ebm_classic_run_multi`` / ``ebm_miz_run_multi``: one host thread + stream per GPU inside the
-    library, members dealt in ``packet``-member packets (default 32) after a sort by cost; no field outputs."""
+    library, members dealt in ``packet``-member packets (default 32) after a sort by cost; no field outputs.
+
+    ``classic_stencil=1`` (classic only, an extension -- SURVEY 8f-4): kappa from the generic flux-form stencil
+    (src/infrastructure.jl:500-527) instead of ``get_diffop(nx)``, i.e. the classic model on non-uniform grids; the
+    default 0 reproduces the reference, which uses ``get_diffop`` whatever the grid (src/classic.jl:21)."""
     name = model_name(model)
     lib = _lib.load()
     nx, nt, dur = st.nx, st.nt, st.dur
@@ -137,7 +141,7 @@ def integrate_arrays(model, st: SpaceTime, forc, par, state, *, lastonly: bool =
         arrs[k] = a
     grid = _lib.make_grid(st)
     opt = _lib.make_options(device, lastonly, field_stride, strict, years_per_launch, newton_maxit, newton_tol,
-                            step_limit, start_year)
+                            step_limit, start_year, classic_stencil)
     multi = None
     if devices is not None:
         if field_stride > 0:

@@ -34,7 +34,7 @@ int main(void) {
     forc[m].base = forc[m].peak = forc[m].cool = F;                   /* Forcing(F) */
     for (int j = 0; j < NX; ++j) { E0[m * NX + j] = 98.0; Tg0[m * NX + j] = 10.0; }
   }
-  ebm_options_t opt = {-1, 1, 0, 0, 0, 0, 0.0, 0, 0};
+  ebm_options_t opt = {-1, 1, 0, 0, 0, 0, 0.0, 0, 0, 0};
   ebm_classic_outputs_t out = {diag, NULL, NULL, Ef, Tgf, NULL};
   printf("%s, %d device(s)\n", ebm_version(), ebm_device_count());
   const int32_t rc = ebm_classic_run(&grid, NMEM, par, forc, E0, Tg0, &opt, &out);

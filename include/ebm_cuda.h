@@ -96,6 +96,10 @@ typedef struct ebm_options {
                                parity is not defined even for the reference itself. */
   int32_t start_year;       /* years already simulated before this run (restart): Forcing is evaluated at
                                T + start_year; output slots stay indexed from the start of this run */
+  int32_t classic_stencil;  /* classic only.  0: kappa from get_diffop(nx) whatever the grid -- what the reference does
+                               (src/classic.jl:21), correct on SpaceTime{identity} only; 1 (extension): kappa
+                               from the generic flux-form stencil of src/infrastructure.jl:500-527, i.e. the classic model
+                               on non-uniform grids (on the identity grid both agree to rounding) */
 } ebm_options_t;
 
 /* ---- outputs (host entry points).  Any pointer may be NULL = not wanted. ------------------------

@@ -38,7 +38,7 @@ struct CGrid
 end
 struct COptions
     device::Int32; lastonly::Int32; field_stride::Int32; strict::Int32; years_per_launch::Int32
-    newton_maxit::Int32; newton_tol::Float64; step_limit::Int32; start_year::Int32
+    newton_maxit::Int32; newton_tol::Float64; step_limit::Int32; start_year::Int32; classic_stencil::Int32
 end
 struct CMulti          # ebm_multi_t
     ndevices::Int32; diag_device::Int32; packet::Int32; reserved::Int32; devices::Ptr{Int32}
@@ -77,7 +77,8 @@ the per-member-year scalar diagnostics `diag[4, 3, dur, nmem]`, final states, fl
 function integrate(model::Symbol, st::SpaceTime{F}, forcings::AbstractVector{<:Forcing},
                    pars::AbstractVector{Collection{Float64}}, inits::AbstractVector{Collection{Vec}};
                    lastonly::Bool=true, field_stride::Int=1, debug::Union{Expr,Nothing}=nothing,
-                   verbose::Bool=false, device::Int=-1, devices::Union{Nothing,AbstractVector{<:Integer}}=nothing) where F
+                   verbose::Bool=false, device::Int=-1, devices::Union{Nothing,AbstractVector{<:Integer}}=nothing,
+                   classic_stencil::Int=0) where F   # 1: generic flux-form stencil in kappa (classic on non-uniform grids)
     isnothing(debug) || throw(ArgumentError("`debug::Expr` cannot be evaluated on the device"))
     model in (:Classic, :MIZ) || throw(MethodError(EBM.Infrastructure.step!, (Val(model),)))
     nmem = length(pars)
@@ -98,7 +99,7 @@ function integrate(model::Symbol, st::SpaceTime{F}, forcings::AbstractVector{<:F
     raw = fill(NaN, nx, nvar, nraw, max(nsel, 1))
     flags = zeros(Int32, nmem)
     x, t = st.x, st.t
-    opt = Ref(COptions(device, lastonly, field_stride, 0, 0, 0, 0.0, 0, 0))
+    opt = Ref(COptions(device, lastonly, field_stride, 0, 0, 0, 0.0, 0, 0, classic_stencil))
     local final, stats
     GC.@preserve x t forc diag seasonal raw flags devs begin
         mopt = Ref(CMulti(length(devs), -1, 0, 0, multi ? pointer(devs) : Ptr{Int32}(C_NULL)))

@@ -80,8 +80,10 @@ def diag(T, E, phi, x):
 
 
 def classic_run(x, t, dur, winter_inx, summer_inx, par, forc, E0, Tg0, *, solver=SOLVE_TRIDIAG,
-                lastonly=True, want_raw=False, want_seasonal=False, nthreads=0):
-    """Returns dict(E, Tg[, raw[nmem,nraw,3,nx]][, seasonal[nmem,dur,3,3,nx]]); inputs untouched."""
+                lastonly=True, want_raw=False, want_seasonal=False, nthreads=0, stencil=0):
+    """Returns dict(E, Tg[, raw[nmem,nraw,3,nx]][, seasonal[nmem,dur,3,3,nx]]); inputs untouched.
+    ``stencil=1``: kappa from the generic flux-form stencil (infrastructure.jl:510-524) instead of get_diffop(nx) --
+    the extension for classic on non-uniform grids (the reference uses get_diffop whatever the grid, classic.jl:21)."""
     x, t = _c(x), _c(t)
     nx, nt = len(x), len(t)
     par = _c(par).reshape(-1, CLASSIC_NPAR)
@@ -93,7 +95,7 @@ def classic_run(x, t, dur, winter_inx, summer_inx, par, forc, E0, Tg0, *, solver
     raw = np.empty((nmem, nraw, CLASSIC_NVAR, nx)) if want_raw else None
     seas = np.empty((nmem, dur, 3, CLASSIC_NVAR, nx)) if want_seasonal else None
     rc = lib().ebm_oracle_classic_run(nx, nt, dur, _p(x), _p(t), winter_inx, summer_inx, nmem, _p(par), _p(forc),
-                                      _p(E), _p(Tg), solver, int(lastonly), _p(raw), _p(seas), nthreads)
+                                      _p(E), _p(Tg), int(solver) | (int(bool(stencil)) << 8), int(lastonly), _p(raw), _p(seas), nthreads)
     if rc != 0:
         raise RuntimeError(f"oracle classic_run failed: {rc}")
     return dict(E=E, Tg=Tg, raw=raw, seasonal=seas)

@@ -142,13 +142,14 @@ typedef struct {
   double dt, cg_tau, dt_tau, dc, M, kLf;
   double* aw;    /* [nx] */
   double* S;     /* [nt+1][nx] (column i of the reference's S is row i-1 here) */
-  double* koff;  /* [nx-1] kappa off-diagonal between j and j+1 */
+  double* koff;  /* [nx-1] kappa super-diagonal: row j, column j+1 */
+  double* ksub;  /* [nx-1] kappa sub-diagonal: row j+1, column j (== koff with get_diffop; differs with the generic stencil) */
   double* kdiag; /* [nx] */
 } classic_statics;
 
 /* get_statics, src/classic.jl:16-33 */
 static void classic_statics_init(classic_statics* st, int nx, int nt, const double* x, const double* t,
-                                 const double* p) {
+                                 const double* p, int stencil) {
   st->nx = nx; st->nt = nt;
   st->dt = 1.0 / nt;                         /* infrastructure.jl:128 */
   st->cg_tau = p[OC_cg] / p[OC_tau];         /* :18 */
@@ -159,20 +160,45 @@ static void classic_statics_init(classic_statics* st, int nx, int nt, const doub
   st->aw = (double*)malloc(sizeof(double) * nx);
   st->S = (double*)malloc(sizeof(double) * (size_t)nx * (nt + 1));
   st->koff = (double*)malloc(sizeof(double) * nx);
+  st->ksub = (double*)malloc(sizeof(double) * nx);
   st->kdiag = (double*)malloc(sizeof(double) * nx);
   double* lambda = (double*)malloc(sizeof(double) * nx);
   diffop_lambda(nx, lambda);
   /* kappa = (1+dt_tau)*I - dt*D*diffop/cg  (:21), evaluated as ((dt*D)*diffop)/cg */
   double dtD = st->dt * p[OC_D];
+  /* stencil == 0: get_diffop(nx) whatever the grid, as the reference does (classic.jl:21).
+   * stencil == 1 (extension, SURVEY 8f-4: classic on non-uniform grids): the coefficients of the generic flux-form
+   * stencil (infrastructure.jl:510-524) -- lower lo_j = m-_j / (dx_{j-1/2} (x_{j+1/2} - x_{j-1/2})), upper
+   * hi_j = m+_j / (dx_{j+1/2} (x_{j+1/2} - x_{j-1/2})), zero flux at both ends; the matrix is no longer symmetric. */
+  double* lo = (double*)calloc((size_t)nx, sizeof(double));
+  double* hi = (double*)calloc((size_t)nx, sizeof(double));
+  if (stencil) {
+    double* xe = (double*)malloc(sizeof(double) * (nx + 2));
+    xe[0] = -x[0];
+    for (int j = 0; j < nx; ++j) xe[j + 1] = x[j];
+    xe[nx + 1] = 2 - x[nx - 1];
+    for (int j = 0; j < nx; ++j) {
+      int i = j + 1;
+      double xxph = (xe[i + 1] + xe[i]) / 2.0, xxmh = (xe[i] + xe[i - 1]) / 2.0;
+      double phmmh = xxph - xxmh;
+      if (j > 0) lo[j] = (1.0 - xxmh * xxmh) / ((xe[i] - xe[i - 1]) * phmmh);
+      if (j < nx - 1) hi[j] = (1.0 - xxph * xxph) / ((xe[i + 1] - xe[i]) * phmmh);
+    }
+    free(xe);
+  } else {
+    for (int j = 0; j < nx; ++j) { lo[j] = j > 0 ? lambda[j - 1] : 0.0; hi[j] = j < nx - 1 ? lambda[j] : 0.0; }
+  }
   for (int j = 0; j < nx; ++j) {
-    double lm = j > 0 ? lambda[j - 1] : 0.0, lp = j < nx - 1 ? lambda[j] : 0.0;
+    double lm = lo[j], lp = hi[j];
     /* diffop diagonal = -l3 with l3 = -l1 - l2, l1[j] = -lm (0.0 at j=0), l2[j] = -lp (0.0 at the end) */
     double l1 = j > 0 ? -lm : 0.0, l2 = j < nx - 1 ? -lp : 0.0;
     double l3 = -l1 - l2;
     double dop_diag = -l3;
     st->kdiag[j] = (1 + st->dt_tau) - (dtD * dop_diag) / p[OC_cg];
     if (j < nx - 1) st->koff[j] = -((dtD * lp) / p[OC_cg]);
+    if (j > 0) st->ksub[j - 1] = -((dtD * lm) / p[OC_cg]);
   }
+  free(lo); free(hi);
   for (int j = 0; j < nx; ++j) st->aw[j] = p[OC_a0] - p[OC_a2] * (x[j] * x[j]);   /* :28 */
   /* S = (S0 - S2*x^2) - (S1*cos(2*pi*t)) * x   (:23-24), column nt+1 := column 1 (:25) */
   for (int i = 0; i < nt; ++i) {
@@ -183,15 +209,16 @@ static void classic_statics_init(classic_statics* st, int nx, int nt, const doub
   memcpy(st->S + (size_t)nt * nx, st->S, sizeof(double) * nx);
   free(lambda);
 }
-static void classic_statics_free(classic_statics* st) { free(st->aw); free(st->S); free(st->koff); free(st->kdiag); }
+static void classic_statics_free(classic_statics* st) { free(st->aw); free(st->S); free(st->koff); free(st->ksub); free(st->kdiag); }
 
 /* tridiagonal solve in LU order (what dense LU without row swaps reduces to on a tridiagonal
  * matrix): l = a/w; w' = d - l*c; y' = r - l*y; back x = (y - c*x')/w.  sub[j] couples j and j-1. */
-static void solve_tridiag(int n, const double* off, const double* diag, const double* rhs, double* xout,
+static void solve_tridiag(int n, const double* sub, const double* off, const double* diag, const double* rhs, double* xout,
                           double* w, double* y) {
+  /* sub[j-1]: row j, column j-1; off[j]: row j, column j+1 */
   w[0] = diag[0]; y[0] = rhs[0];
   for (int j = 1; j < n; ++j) {
-    double l = off[j - 1] / w[j - 1];
+    double l = sub[j - 1] / w[j - 1];
     w[j] = diag[j] - l * off[j - 1];
     y[j] = rhs[j] - l * y[j - 1];
   }
@@ -257,13 +284,13 @@ static void classic_step(const classic_statics* st, const double* p, int i1, dou
     double* A = (double*)calloc((size_t)nx * nx, sizeof(double));
     for (int j = 0; j < nx; ++j) {
       A[(size_t)j * nx + j] = diag[j];
-      if (j < nx - 1) { A[(size_t)j * nx + j + 1] = st->koff[j]; A[(size_t)(j + 1) * nx + j] = st->koff[j]; }
+      if (j < nx - 1) { A[(size_t)j * nx + j + 1] = st->koff[j]; A[(size_t)(j + 1) * nx + j] = st->ksub[j]; }
     }
     solve_dense_lu(nx, A, rhs);
     memcpy(Tg, rhs, sizeof(double) * nx);
     free(A);
   } else {
-    solve_tridiag(nx, st->koff, diag, rhs, Tg, w, y);
+    solve_tridiag(nx, st->ksub, st->koff, diag, rhs, Tg, w, y);
   }
 }
 
@@ -273,6 +300,8 @@ int ebm_oracle_classic_run(int nx, int nt, int dur, const double* x, const doubl
                            double* E, double* Tg, int solver, int lastonly,
                            double* raw, double* seasonal, int nthreads) {
   if (nx < 2 || nt < 1 || dur < 1 || nmem < 0) return -1;
+  const int stencil = (solver >> 8) & 1;   /* bit 8 of `solver`: generic flux-form stencil in kappa (extension) */
+  solver &= 0xff;
   const size_t fsz = (size_t)OCV_NVAR * nx;
   const size_t nraw = lastonly ? (size_t)nt : (size_t)nt * dur;
   const double dt = 1.0 / nt;
@@ -286,7 +315,7 @@ int ebm_oracle_classic_run(int nx, int nt, int dur, const double* x, const doubl
     const double* p = par + (size_t)m * OC_NPAR;
     const double* fr = forc + (size_t)m * OF_NF;
     classic_statics st;
-    classic_statics_init(&st, nx, nt, x, t, p);
+    classic_statics_init(&st, nx, nt, x, t, p, stencil);
     double* cur = (double*)malloc(sizeof(double) * fsz);
     double* work = (double*)malloc(sizeof(double) * 4 * nx);
     sampler_t s = {nx, nt, dur, OCV_NVAR, winter_inx, summer_inx, lastonly, NULL, NULL, NULL};

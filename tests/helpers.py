@@ -28,12 +28,12 @@ def cold_init(nx):
     return ebm.Collection(E=np.full(nx, -9.5), Tg=np.full(nx, -10.0))
 
 
-def oracle_classic(st, forcings, pars, inits, *, lastonly=True, raw=False, seasonal=False, solver=0, nthreads=0):
+def oracle_classic(st, forcings, pars, inits, *, lastonly=True, raw=False, seasonal=False, solver=0, nthreads=0, stencil=0):
     E0 = np.stack([np.asarray(i["E"], float) for i in inits])
     Tg0 = np.stack([np.asarray(i["Tg"], float) for i in inits])
     return oracle.classic_run(st.x, st.t, st.dur, st.winter.inx, st.summer.inx, classic_rows(pars),
                               forcing_rows(forcings), E0, Tg0, solver=solver, lastonly=lastonly, want_raw=raw,
-                              want_seasonal=seasonal, nthreads=nthreads)
+                              want_seasonal=seasonal, nthreads=nthreads, stencil=stencil)
 
 
 def oracle_miz(st, forcings, pars, inits, *, T0=None, lastonly=True, raw=False, seasonal=False, nthreads=0, tol=1e-8):

@@ -61,13 +61,16 @@ def crossmean(rows: np.ndarray) -> np.ndarray:
 
 
 # --------------------------------------------------------------------------- classic
-def classic_statics(x, t, nt, par):
+def classic_statics(x, t, nt, par, stencil=0):
+    """get_statics (classic.jl:16-33).  ``stencil=1``: the generic flux-form stencil (infrastructure.jl:505-526) in kappa
+    instead of get_diffop(nx) -- the extension for non-uniform grids."""
     nx = len(x)
     dt = 1.0 / nt
     cg_tau = par["cg"] / par["tau"]
     dt_tau = dt / par["tau"]
     dc = dt_tau * cg_tau
-    kappa = (1 + dt_tau) * np.eye(nx) - dt * par["D"] * get_diffop(nx) / par["cg"]
+    dop = diffusion_matrix(x, 1.0, 1, generic_stencil_cache(x)) if stencil else get_diffop(nx)
+    kappa = (1 + dt_tau) * np.eye(nx) - dt * par["D"] * dop / par["cg"]
     S = (par["S0"] - par["S2"] * x**2)[:, None] - (par["S1"] * np.cos(2.0 * PI * t))[None, :] * x[:, None]
     S = np.hstack([S, S[:, :1]])
     M = par["B"] + cg_tau
@@ -95,9 +98,9 @@ def classic_step(stat, par, i, f, E, Tg):
     return E, Tg, T, h
 
 
-def classic_integrate(st, forcing, par, E0, Tg0):
+def classic_integrate(st, forcing, par, E0, Tg0, stencil=0):
     """integrate(:Classic, ...) storing every step (lastonly=false).  Returns dict of [nt*dur, nx]."""
-    stat = classic_statics(st.x, st.t, st.nt, par)
+    stat = classic_statics(st.x, st.t, st.nt, par, stencil)
     E, Tg = E0.copy(), Tg0.copy()
     n = st.nt * st.dur
     out = {k: np.empty((n, st.nx)) for k in ("E", "T", "h", "Tg")}

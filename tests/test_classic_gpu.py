@@ -419,3 +419,34 @@ np.save(sys.argv[1], np.concatenate([r.final["E"].ravel(), r.final["Tg"].ravel()
         (a, la), (b, lb) = outs
         assert np.array_equal(a, b)
         assert la > lb    # the balanced path really ran: many chunked launches instead of a few
+
+
+@pytest.mark.parametrize("xfunc,nx", [("sin", 100), ("sin", 60), ("identity", 100), ("sin", 180)])
+def test_generic_stencil_extension(xfunc, nx):
+    """ebm_options_t.classic_stencil = 1: the classic model with the generic flux-form stencil in kappa --
+    a non-symmetric tridiagonal matrix on non-uniform grids.  Fast kernel (table-driven and per-member-coefficient
+    instances, 8 and 16 bands) within tolerance of the oracle, literal kernel bit-identical; the default (0) keeps the
+    reference's behaviour (get_diffop whatever the grid)."""
+    nmem = 36
+    st = ebm.SpaceTime(nx, 2000, 2, xfunc)
+    forcings = [ebm.Forcing(-10.0 + 20.0 * m / (nmem - 1)) for m in range(nmem)]
+    pars = [_par(B=2.0 + 0.05 * (m % 4)) if m < 32 else _par(D=0.5 + 0.05 * (m % 4)) for m in range(nmem)]   # last group: per-member D
+    inits = [warm_init(nx) if m % 2 == 0 else cold_init(nx) for m in range(nmem)]
+    o = oracle_classic(st, forcings, pars, inits, raw=True, seasonal=True, stencil=1)
+    state = {"E": np.stack([i.E for i in inits]), "Tg": np.stack([i.Tg for i in inits])}
+    from helpers import classic_rows
+    r = ebm.integrate_arrays("Classic", st, forcing_rows(forcings), classic_rows(pars), state, field_stride=5, classic_stencil=1)
+    assert r.flags.max() == 0
+    tol = TOL if nx <= 100 else 1e-8
+    assert_close(r.final["E"], o["E"], tol, "final E")
+    assert_close(r.final["Tg"], o["Tg"], tol, "final Tg")
+    sel = np.arange(0, nmem, 5)
+    assert_close(r.raw, o["raw"][sel], tol, "raw")
+    assert_close(r.diag[..., :2], oracle_diag_classic(o["seasonal"], st.x)[..., :2], tol, "diag")
+    rs = ebm.integrate_arrays("Classic", st, forcing_rows(forcings[:4]), classic_rows(pars[:4]), {k: v[:4] for k, v in state.items()},
+                              strict=True, classic_stencil=1)
+    assert np.array_equal(rs.final["E"], o["E"][:4]) and np.array_equal(rs.final["Tg"], o["Tg"][:4])
+    if xfunc == "sin":       # the default still reproduces the reference's behaviour on this grid
+        od = oracle_classic(st, forcings[:4], pars[:4], inits[:4])
+        rd = ebm.integrate_arrays("Classic", st, forcing_rows(forcings[:4]), classic_rows(pars[:4]), {k: v[:4] for k, v in state.items()})
+        assert_close(rd.final["E"], od["E"], tol, "default stencil")

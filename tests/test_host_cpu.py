@@ -297,14 +297,15 @@ def test_multi_struct_layout_and_no_gpu_behaviour():
 #include <stdio.h>
 #include <stddef.h>
 #include "ebm_cuda.h"
-int main(void) { printf("%zu %zu %zu %zu\n", sizeof(ebm_multi_t), offsetof(ebm_multi_t, diag_device), offsetof(ebm_multi_t, packet), offsetof(ebm_multi_t, devices)); return 0; }"""
+int main(void) { printf("%zu %zu %zu %zu %zu %zu\n", sizeof(ebm_multi_t), offsetof(ebm_multi_t, diag_device), offsetof(ebm_multi_t, packet), offsetof(ebm_multi_t, devices), sizeof(ebm_options_t), offsetof(ebm_options_t, classic_stencil)); return 0; }"""
     r = subprocess.run(["gcc", "-x", "c", "-", "-I", os.path.join(ROOT, "include"), "-o", exe], input=code, text=True, capture_output=True)
     assert r.returncode == 0, r.stderr
     try:
         got = list(map(int, subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()))
     finally:
         os.remove(exe)
-    assert got == [C.sizeof(_lib.Multi), _lib.Multi.diag_device.offset, _lib.Multi.packet.offset, _lib.Multi.devices.offset]
+    assert got == [C.sizeof(_lib.Multi), _lib.Multi.diag_device.offset, _lib.Multi.packet.offset, _lib.Multi.devices.offset,
+                   C.sizeof(_lib.Options), _lib.Options.classic_stencil.offset]
     if _no_gpu():
         st = ebm.SpaceTime(100, 2000, 1)
         p = ebm.default_parameters("Classic")

@@ -266,3 +266,25 @@ def test_c5_blow_up_members_blow_up_in_the_independent_restatement_too():
             blew = True                                   # closure residual is NaN: no convergence, or a singular Jacobian
         assert blew == blows, (m, blows)
     assert rows[0][order.index("m1")] > 0 and rows[1][order.index("ai")] < 0.4
+
+
+def test_classic_generic_stencil_extension():
+    """SURVEY 8f-4 (an extension: the reference's classic model uses get_diffop(nx) whatever the grid, classic.jl:21):
+    kappa from the generic flux-form stencil (infrastructure.jl:500-527).  On the identity grid the two operators agree
+    to rounding, so the runs agree far inside the tolerance; on a sin grid the oracle (tridiagonal solve with distinct
+    sub/super diagonals) agrees with its dense-LU variant and with the independent NumPy restatement."""
+    par = ebm.default_parameters("Classic")
+    f = ebm.Forcing(0.0)
+    st = ebm.SpaceTime(100, 2000, 1)
+    a = oracle_classic(st, [f], [par], [warm_init(100)])
+    b = oracle_classic(st, [f], [par], [warm_init(100)], stencil=1)
+    assert rel_err(b["E"], a["E"]).max() < 1e-10 and rel_err(b["Tg"], a["Tg"]).max() < 1e-10
+    sts = ebm.SpaceTime(60, 1000, 1, "sin")
+    c = oracle_classic(sts, [f], [par], [warm_init(60)], stencil=1, lastonly=False, raw=True)
+    d = oracle_classic(sts, [f], [par], [warm_init(60)], stencil=1, solver=oracle.SOLVE_DENSE_LU)
+    assert rel_err(d["E"], c["E"]).max() < 1e-10
+    r = npr.classic_integrate(sts, f, par, np.full(60, 98.0), np.full(60, 10.0), stencil=1)
+    for vi, v in enumerate(("E", "T", "h")):
+        assert rel_err(r[v], c["raw"][0, :, vi]).max() < 1e-9, v
+    ref_behaviour = oracle_classic(sts, [f], [par], [warm_init(60)])          # get_diffop on the sin grid: what the reference does
+    assert np.abs(ref_behaviour["E"] - c["E"]).max() > 1.0                    # ... a different model
