@@ -136,6 +136,8 @@ def make_multi(ndevices=0, devices=None, diag_device=-1, packet=0) -> Multi:
     """ebm_multi_t: GPUs of one *_run_multi call (0 = all visible), where the diagnostics go, packet size."""
     arr = None
     if devices is not None:
+        if len(set(devices)) != len(devices) or min(devices, default=0) < 0:
+            raise ValueError(f"devices must be distinct non-negative CUDA ordinals, got {list(devices)}")
         arr = (C.c_int32 * len(devices))(*devices)
         ndevices = len(devices)
     m = Multi(ndevices, diag_device, packet, 0, C.cast(arr, _i32p) if arr is not None else None)

@@ -183,6 +183,20 @@ struct GatherHook : EbmDiagHook {
   }
 };
 
+// Field outputs (seasonal / raw) of the members a device holds: the selected ones (global index % field_stride == 0) are
+// integrated once more as a small sub-ensemble with field_stride = 1 -- a member's arithmetic does not depend on its
+// neighbours, so the fields belong bit for bit to the run that produced the diagnostics -- and their rows land at
+// global index / field_stride in the caller's arrays.
+struct FieldSel {
+  std::vector<long long> local, slot;   // position in the device's sub-ensemble, row in the caller's field arrays
+  FieldSel(const std::vector<long long>& ix, int stride, bool wanted) {
+    if (!wanted || stride <= 0) return;
+    for (size_t r = 0; r < ix.size(); ++r)
+      if (ix[r] % stride == 0) { local.push_back((long long)r); slot.push_back(ix[r] / stride); }
+  }
+  bool any() const { return !local.empty(); }
+};
+
 struct ThreadResult { int rc = EBM_OK; std::string err; };
 
 // runs `work(rank)` on one thread per device; returns the first failure
@@ -227,7 +241,6 @@ extern "C" int32_t ebm_classic_run_multi(const ebm_grid_t* grid, int64_t nmem, c
                                          const ebm_forcing_t* forc, const double* E0, const double* Tg0,
                                          const ebm_options_t* opt_in, const ebm_multi_t* multi, ebm_classic_outputs_t* out) {
   if (!grid || nmem < 1 || !par || !forc || !E0 || !Tg0 || !out) { ebm_set_error("classic_run_multi: NULL argument or nmem < 1"); return EBM_ERR_INVALID; }
-  if (out->seasonal || out->raw) { ebm_set_error("classic_run_multi: field outputs (seasonal / raw) are single-GPU options"); return EBM_ERR_UNSUPPORTED; }
   std::vector<int> devs;
   int rc = resolve_devices(multi, &devs);
   if (rc != EBM_OK) return rc;
@@ -278,6 +291,25 @@ extern "C" int32_t ebm_classic_run_multi(const ebm_grid_t* grid, int64_t nmem, c
     put_rows(out->E_final, ef, ix, (size_t)nx);
     put_rows(out->Tg_final, tf, ix, (size_t)nx);
     put_rows(out->flags, fl, ix, 1);
+    const FieldSel fs(ix, opt_in ? opt_in->field_stride : 0, out->seasonal || out->raw);
+    if (fs.any()) {
+      const size_t ns = fs.local.size(), nraw = (size_t)(op.lastonly ? grid->nt : (long long)grid->nt * grid->dur);
+      const size_t lenS = (size_t)grid->dur * EBM_NSEASON * EBM_CLASSIC_NVAR * nx, lenR = nraw * EBM_CLASSIC_NVAR * nx;
+      auto p2 = take_rows(p.data(), fs.local, EBM_CLASSIC_NPAR);
+      auto f2 = take_rows(f.data(), fs.local, EBM_NFORCING);
+      auto e2 = take_rows(e.data(), fs.local, (size_t)nx), t2 = take_rows(t.data(), fs.local, (size_t)nx);
+      std::vector<double> se(out->seasonal ? ns * lenS : 0), rw(out->raw ? ns * lenR : 0);
+      ebm_classic_outputs_t o2;
+      memset(&o2, 0, sizeof(o2));
+      o2.seasonal = out->seasonal ? se.data() : nullptr;
+      o2.raw = out->raw ? rw.data() : nullptr;
+      op.field_stride = 1;
+      const int r2 = ebm_classic_run(grid, (int64_t)ns, (const ebm_classic_params_t*)p2.data(), (const ebm_forcing_t*)f2.data(),
+                                     e2.data(), t2.data(), &op, &o2);
+      if (r2 != EBM_OK) return r2;
+      put_rows(out->seasonal, se, fs.slot, lenS);
+      put_rows(out->raw, rw, fs.slot, lenR);
+    }
     return EBM_OK;
   });
 }
@@ -287,7 +319,6 @@ extern "C" int32_t ebm_miz_run_multi(const ebm_grid_t* grid, int64_t nmem, const
                                      const double* D0, const double* phi0, const double* T0guess,
                                      const ebm_options_t* opt_in, const ebm_multi_t* multi, ebm_miz_outputs_t* out) {
   if (!grid || nmem < 1 || !par || !forc || !Ei0 || !Ew0 || !h0 || !D0 || !phi0 || !out) { ebm_set_error("miz_run_multi: NULL argument or nmem < 1"); return EBM_ERR_INVALID; }
-  if (out->seasonal || out->raw) { ebm_set_error("miz_run_multi: field outputs (seasonal / raw) are single-GPU options"); return EBM_ERR_UNSUPPORTED; }
   std::vector<int> devs;
   int rc = resolve_devices(multi, &devs);
   if (rc != EBM_OK) return rc;
@@ -342,6 +373,26 @@ extern "C" int32_t ebm_miz_run_multi(const ebm_grid_t* grid, int64_t nmem, const
     put_rows(out->newton_iters, it, ix, 1);
     put_rows(out->nonconv, nc, ix, 1);
     put_rows(out->flags, fl, ix, 1);
+    const FieldSel fs(ix, opt_in ? opt_in->field_stride : 0, out->seasonal || out->raw);
+    if (fs.any()) {
+      const size_t ns = fs.local.size(), nraw = (size_t)(op.lastonly ? grid->nt : (long long)grid->nt * grid->dur);
+      const size_t lenS = (size_t)grid->dur * EBM_NSEASON * EBM_MIZ_NVAR * nx, lenR = nraw * EBM_MIZ_NVAR * nx;
+      auto p2 = take_rows(p.data(), fs.local, EBM_MIZ_NPAR);
+      auto f2 = take_rows(f.data(), fs.local, EBM_NFORCING);
+      std::vector<double> in2[6];
+      for (int k = 0; k < 6; ++k) if (init[k]) in2[k] = take_rows(in[k].data(), fs.local, (size_t)nx);
+      std::vector<double> se(out->seasonal ? ns * lenS : 0), rw(out->raw ? ns * lenR : 0);
+      ebm_miz_outputs_t o2;
+      memset(&o2, 0, sizeof(o2));
+      o2.seasonal = out->seasonal ? se.data() : nullptr;
+      o2.raw = out->raw ? rw.data() : nullptr;
+      op.field_stride = 1;
+      const int r2 = ebm_miz_run(grid, (int64_t)ns, (const ebm_miz_params_t*)p2.data(), (const ebm_forcing_t*)f2.data(), in2[0].data(),
+                                 in2[1].data(), in2[2].data(), in2[3].data(), in2[4].data(), init[5] ? in2[5].data() : nullptr, &op, &o2);
+      if (r2 != EBM_OK) return r2;
+      put_rows(out->seasonal, se, fs.slot, lenS);
+      put_rows(out->raw, rw, fs.slot, lenR);
+    }
     return EBM_OK;
   });
 }

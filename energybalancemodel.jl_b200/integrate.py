@@ -144,8 +144,6 @@ def integrate_arrays(model, st: SpaceTime, forc, par, state, *, lastonly: bool =
                             step_limit, start_year, classic_stencil)
     multi = None
     if devices is not None:
-        if field_stride > 0:
-            raise ValueError("field outputs (field_stride > 0) are single-GPU options")
         multi = _lib.make_multi(devices=list(devices), packet=packet) if not isinstance(devices, int) else _lib.make_multi(ndevices=devices, packet=packet)
     nsel = (nmem + field_stride - 1) // field_stride if field_stride > 0 else 0
     nraw = nt if lastonly else nt * dur

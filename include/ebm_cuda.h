@@ -191,7 +191,8 @@ int32_t ebm_miz_step(const ebm_grid_t* grid, const ebm_miz_params_t* par, int32_
  * Members are independent (src/infrastructure.jl:615-636 integrates one member; nothing couples two), so the path
  * shards with no data-path collective.  Single process, one host thread + stream per GPU; members are dealt to
  * the GPUs in packets after a stable sort by what they cost (classic: regime of the initial state).  Every output
- * row comes back at the member's original index.  seasonal / raw (per-member field outputs) must be NULL.       */
+ * row comes back at the member's original index; seasonal / raw rows belong to the members whose ORIGINAL index is a
+ * multiple of field_stride, in that order, exactly as in the single-GPU call.                                    */
 typedef struct ebm_multi {
   int32_t ndevices;       /* GPUs to use; 0 = every visible device */
   int32_t diag_device;    /* -1: out->diag is host memory, every GPU copies its own rows back;

@@ -84,9 +84,8 @@ function integrate(model::Symbol, st::SpaceTime{F}, forcings::AbstractVector{<:F
     nmem = length(pars)
     (nmem > 0 && length(forcings) == nmem == length(inits)) || throw(ArgumentError("forcings, pars, inits must have equal non-zero length"))
     # devices = [0, 1, ...]: several GPUs behind one call (ebm_*_run_multi: one host thread + stream per GPU inside
-    # the library, members dealt in 32-member packets after a sort by cost); diagnostics, final state and flags only
+    # the library, members dealt in 32-member packets after a sort by cost); every output as in the single-GPU call
     multi = !isnothing(devices)
-    multi && (field_stride = 0)
     devs = multi ? Int32.(collect(devices)) : Int32[]
     nx, nt, dur = st.nx, st.nt, st.dur
     nsel = field_stride > 0 ? cld(nmem, field_stride) : 0

@@ -362,10 +362,13 @@ def test_multi_gpu_entry_point_matches_single_gpu_bitwise(diag_on_device):
     forc = np.zeros((nmem, 10)); forc[:, :3] = np.linspace(-15.0, 15.0, nmem)[:, None]
     warm = (np.arange(nmem) % 3) != 0
     state = {"E": np.where(warm[:, None], 98.0, -9.5) * np.ones((nmem, nx)), "Tg": np.where(warm[:, None], 10.0, -10.0) * np.ones((nmem, nx))}
-    ref = ebm.integrate_arrays("Classic", st, forc, par, state)
+    ref = ebm.integrate_arrays("Classic", st, forc, par, state, field_stride=7)
     if not diag_on_device:
-        r = ebm.integrate_arrays("Classic", st, forc, par, state, devices=list(range(ndev)), packet=16)
+        r = ebm.integrate_arrays("Classic", st, forc, par, state, devices=list(range(ndev)), packet=16, field_stride=7)
         assert np.array_equal(r.diag, ref.diag)
+        # field outputs: rows of the members whose ORIGINAL index is a multiple of the stride, whatever GPU ran them
+        assert r.seasonal.shape == ref.seasonal.shape and np.array_equal(r.seasonal, ref.seasonal, equal_nan=True)
+        assert np.array_equal(r.raw, ref.raw, equal_nan=True)
     else:
         lib = _lib.load()
         d_diag = torch.full((nmem, years, 3, 4), float("nan"), dtype=torch.float64, device="cuda:0")

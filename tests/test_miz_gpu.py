@@ -197,6 +197,25 @@ def test_ensemble_strict_bitwise_and_fast_short_horizon(nmem, nx, nt, xfunc):
     _check(r.raw[:, :HORIZON], o["raw"][sel, :HORIZON], "raw")
 
 
+def test_multi_gpu_entry_point_matches_single_gpu_bitwise():
+    """ebm_miz_run_multi (members dealt over the GPUs in packets): diagnostics, final state, counters, flags and the
+    strided members' field outputs equal the single-GPU call's bit for bit.  Runs on one GPU too."""
+    import torch
+    ndev = min(torch.cuda.device_count(), 2)
+    nmem, nx = 75, 60
+    st = ebm.SpaceTime(nx, 400, 1, "sin")
+    forcings, pars = _ensemble(nmem)
+    inits = [_zero(nx) for _ in range(nmem)]
+    ref = ebm.integrate_ensemble("MIZ", st, forcings, pars, inits, field_stride=4)
+    r = ebm.integrate_ensemble("MIZ", st, forcings, pars, inits, field_stride=4, devices=list(range(ndev)), packet=8)
+    assert _same(r.diag, ref.diag)
+    for k in STATE + ("T0",):
+        assert _same(r.final[k], ref.final[k]), k
+    assert np.array_equal(r.newton_iters, ref.newton_iters) and np.array_equal(r.nonconv, ref.nonconv)
+    assert np.array_equal(r.flags, ref.flags)
+    assert r.seasonal.shape == ref.seasonal.shape and _same(r.seasonal, ref.seasonal) and _same(r.raw, ref.raw)
+
+
 def test_sampler_self_consistency_and_diagnostics():
     """savesol! semantics on the device (infrastructure.jl:549-591): winter / summer snapshots are the raw steps
     winter.inx / summer.inx, the annual mean is the mean of the year's raw steps, and the L0 diagnostics equal
