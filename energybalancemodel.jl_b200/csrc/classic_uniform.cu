@@ -97,7 +97,7 @@ struct RowStore {
   }
 };
 
-template <int K, int WB, int MW, bool QS_SMEM, bool WARPM, bool TAB>
+template <int K, int WB, int MW, bool QS_SMEM, bool WARPM, bool TAB, bool UPAR>
 struct Ctx {
   static constexpr int NXP = K * WB;
   // tables / scratch in shared memory
@@ -120,7 +120,18 @@ struct Ctx {
     return c;
   }
   // member constants
-  double A, Fb, ai, cg_tau, M, kLf, inv_cw, dt, dt_tau, dttau_cw, dc, inv_nt, inv_Lf;
+  // (UPAR: every member of the launch has the same 15 parameters -- the constants below are then read from the kernel
+  // argument block, i.e. they are constant-bank operands of the FP64 instructions instead of 26 live registers)
+  double A_, Fb_, ai_, cg_tau_, M_, kLf_, inv_cw_, dt_, dt_tau_, dttau_cw_, dc_, inv_nt_, inv_Lf_;
+#define EBM_MEMBER_CONSTS(a)                                                                                        \
+  const double A = UPAR ? (a).u.A : A_, Fb = UPAR ? (a).u.Fb : Fb_, ai = UPAR ? (a).u.ai : ai_,                     \
+               cg_tau = UPAR ? (a).u.cg_tau : cg_tau_, M = UPAR ? (a).u.M : M_, kLf = UPAR ? (a).u.kLf : kLf_,      \
+               inv_cw = UPAR ? (a).u.inv_cw : inv_cw_, dt = UPAR ? (a).u.dt : dt_,                                  \
+               dt_tau = UPAR ? (a).u.dt_tau : dt_tau_, dttau_cw = UPAR ? (a).u.dttau_cw : dttau_cw_,                \
+               dc = UPAR ? (a).u.dc : dc_, inv_nt = UPAR ? (a).u.inv_nt : inv_nt_,                                  \
+               inv_Lf = UPAR ? (a).u.inv_Lf : inv_Lf_;                                                              \
+  (void)A; (void)Fb; (void)ai; (void)cg_tau; (void)M; (void)kLf; (void)inv_cw; (void)dt; (void)dt_tau;              \
+  (void)dttau_cw; (void)dc; (void)inv_nt; (void)inv_Lf
   // thread identity
   int band, mi, j0;
   // index of cell i of this thread in the per-cell shared arrays (annual sums): [cell][member] when a warp holds
@@ -145,6 +156,7 @@ struct Ctx {
   __device__ __forceinline__ void sample(const ClassicKArgs& a, const int i, const double wj, const double En,
                                          const double T, const int season, const int ti, const int year,
                                          double& se, double& dgT, double& dgE, double& dgA, double& dgX) {
+    EBM_MEMBER_CONSTS(a);
     se += En;                                   // running annual sum of E of this cell (caller loads / stores it)
     const double sEi = se;
     accT = fma(wj, T, accT);
@@ -184,12 +196,45 @@ struct Ctx {
     }
   }
 
-  static constexpr int GI = 3;
+  // Pad cells (a band's cells beyond nx; decoupled rows of weight 0) follow the band's real cells: ice when every one
+  // of them is ice at the turn of the year, open water otherwise -- so that they do not decide which code path the band takes (a snowball's polar band
+  // would otherwise run the mixed ice / water code for its pad cells alone and hold the CTA's other warps at the
+  // barrier).  Their tables (TAB) make both states self-sustaining over a year.  Called at launch and at the end of every
+  // year, and it resets the pad cells unconditionally: their state, hence the code path of every step, is a function of
+  // the real cells' state at the last year boundary -- launches split at year boundaries stay bit-identical.
+  __device__ __forceinline__ void set_pads(const ClassicKArgs& a) {
+    EBM_MEMBER_CONSTS(a);
+    const int nv = a.nx - j0;
+    if (TAB && nv < K && nv > 0) {
+      int hand = -1;
+#pragma unroll
+      for (int i = 0; i < K; ++i) if (i < nv) hand &= __double2hiint(E[i]);
+      const bool wantice = hand < 0;
+#pragma unroll
+      for (int i = 0; i < K; ++i) {
+        if (i >= nv) {
+          E[i] = wantice ? -10.0 : 100.0; Tg[i] = wantice ? -10.0 : 10.0;
+          rs.r(i) = E[i] * fast_rcp(fma(M, E[i], -kLf));
+        }
+      }
+    }
+  }
+
+#ifndef EBM_GI_UPAR
+#define EBM_GI_UPAR 5
+#endif
+#ifndef EBM_GIM_UPAR
+#define EBM_GIM_UPAR 4
+#endif
+  static constexpr int GI = UPAR ? EBM_GI_UPAR : 3;      // cells per statement-major group: all-ice path
+  static constexpr int GIM = UPAR ? EBM_GIM_UPAR : 3;    // mixed ice / water path
   template <int I0, bool MIXED, bool SLOW>
   __device__ __forceinline__ void ice_group(const ClassicKArgs& a, const double fmA, const double S1c0, const double S1c1,
                                             const int season, const int ti, const int year, bool& anymask,
                                             double& dgT, double& dgE, double& dgA, double& dgX) {
-    constexpr int N = (I0 + GI <= K) ? GI : K - I0;
+    EBM_MEMBER_CONSTS(a);
+    constexpr int GG = MIXED ? GIM : GI;
+    constexpr int N = (I0 + GG <= K) ? GG : K - I0;
     PhysTab p[N]; double rv[N], se[N];
 #pragma unroll
     for (int g = 0; g < N; ++g) { p[g] = phys_at(j0 + I0 + g); rv[g] = rs.r(I0 + g); se[g] = sumE[cidx(I0 + g)]; }
@@ -218,16 +263,16 @@ struct Ctx {
 #pragma unroll
     for (int g = 0; g < N; ++g) {
       const int cneg = __double2hiint(C[g]) >> 31;              // for E < 0: M - kLf/E > 0, so T0 < 0 <=> C < 0
-      const double Ti = __hiloint2double(__double2hiint(T[g]) & cneg, __double2loint(T[g]) & cneg);
       if constexpr (MIXED) {
-        const double Eo = E[I0 + g];
-        // sign of T0 for a water cell (needed when it freezes in this step): sign(C) * sign(M - kLf/E), E > 0
-        const bool wneg = !is_zero(Eo) && ((cneg != 0) != is_neg(fma(M, Eo, -kLf))) && C[g] != 0.0;
-        tneg[g] = ice[g] ? cneg : (wneg ? -1 : 0);
-        T[g] = ice[g] ? Ti : Eo * inv_cw;                                                     //                        :51
+        // T = E/cw [E >= 0] + T0 [E < 0 and T0 < 0]                                              :51
+        // (the sign of T0 of a water cell matters only if the cell freezes in this step: fix-up below)
+        tneg[g] = ice[g] & cneg;
+        const double Tw = E[I0 + g] * inv_cw;
+        T[g] = __hiloint2double((__double2hiint(T[g]) & tneg[g]) | (__double2hiint(Tw) & ~ice[g]),
+                                (__double2loint(T[g]) & tneg[g]) | (__double2loint(Tw) & ~ice[g]));
       } else {
         tneg[g] = cneg;
-        T[g] = Ti;
+        T[g] = __hiloint2double(__double2hiint(T[g]) & cneg, __double2loint(T[g]) & cneg);
       }
     }
 #pragma unroll
@@ -267,6 +312,24 @@ struct Ctx {
     }
 #pragma unroll
     for (int g = 0; g < N; ++g) Tg[I0 + g] = fma(um[g], G[g], S[g]);                          // right-hand side     :58-62
+    if constexpr (MIXED) {
+      // a water cell that froze in this step (rare): its row is masked if T0 = C/(M - kLf/E) of the OLD enthalpy E > 0
+      // was negative, i.e. C != 0 and sign(C) != sign(M E - kLf)                                :50,56,61
+      int frz = 0;
+#pragma unroll
+      for (int g = 0; g < N; ++g) frz |= ~ice[g] & __double2hiint(En[g]);
+      if (frz < 0) {
+#pragma unroll
+        for (int g = 0; g < N; ++g) {
+          const double Eo = E[I0 + g];
+          if (!ice[g] && is_neg(En[g]) && !is_zero(Eo) && C[g] != 0.0 && (is_neg(C[g]) != is_neg(fma(M, Eo, -kLf)))) {
+            um[g] = dt_tau * r[g];
+            Tg[I0 + g] = fma(um[g], G[g], S[g]);
+            anymask = true;
+          }
+        }
+      }
+    }
 #pragma unroll
     for (int g = 0; g < N; ++g) {
       sample<SLOW>(a, I0 + g, p[g].wts, En[g], T[g], season, ti, year, se[g], dgT, dgE, dgA, dgX);
@@ -274,7 +337,7 @@ struct Ctx {
     }
 #pragma unroll
     for (int g = 0; g < N; ++g) {
-      rs.r(I0 + g) = r[g]; rs.q(I0 + g) = cg_tau * um[g];                                    // dc/(M - kLf/E) [masked] :56
+      rs.r(I0 + g) = r[g]; rs.q(I0 + g) = um[g];                // dt_tau/(M - kLf/E) [masked]; times cg_tau in the pivots :56
       sumE[cidx(I0 + g)] = se[g];
     }
   }
@@ -284,19 +347,20 @@ struct Ctx {
                                              double& dgT, double& dgE, double& dgA, double& dgX) {
     if constexpr (I0 < K) {
       ice_group<I0, MIXED, SLOW>(a, fmA, S1c0, S1c1, season, ti, year, anymask, dgT, dgE, dgA, dgX);
-      ice_groups<I0 + GI, MIXED, SLOW>(a, fmA, S1c0, S1c1, season, ti, year, anymask, dgT, dgE, dgA, dgX);
+      ice_groups<I0 + (MIXED ? GIM : GI), MIXED, SLOW>(a, fmA, S1c0, S1c1, season, ti, year, anymask, dgT, dgE, dgA, dgX);
     }
   }
 
   template <bool SLOW>
   __device__ __forceinline__ void step(const ClassicKArgs& a, const double f, const double S1c0, const double S1c1,
                                        const int ti, const int year) {
+    EBM_MEMBER_CONSTS(a);
     const int tid = threadIdx.x;
     const int nx = a.nx, nt = a.nt;
     const double fmA = f - A;
     const double fmAFb = fmA + Fb;
     const int season = SLOW ? ((ti == a.winter_inx) ? 0 : (ti == a.summer_inx) ? 1 : (ti == nt) ? 2 : -1) : -1;
-    // rs.q(i): diagonal decrement dc/(M - kLf/E) of a masked row (else 0); later the pivots / spikes of the band
+    // rs.q(i): dt_tau/(M - kLf/E) of a masked row (else 0): the diagonal decrement over cg_tau; later the pivots / spikes
     bool anymask = !TAB;   // without precomputed pivots every band eliminates in full
     PHASE_BEGIN();
     double dgT = 0.0, dgE = 0.0, dgA = 0.0, dgX = 2.0;
@@ -344,7 +408,7 @@ struct Ctx {
             const double r = En * fast_rcp(fma(M, En, -kLf));
             rs.r(i) = r;
             if (T0 < 0.0) {
-              rs.q(i) = dc * r; anymask = true;
+              rs.q(i) = dt_tau * r; anymask = true;
               Tg[i] = fma(dt_tau * r, fma(ai, fma(-S1c1, p.S1x, p.S0x), fmA), Tgo);
             } else {
               Tg[i] = Tgo;
@@ -393,7 +457,7 @@ struct Ctx {
 #pragma unroll
       for (int i = 0; i < K; ++i) {
         const CoefTab cf = coef_at(j0 + i);
-        const double diag = cf.kjj - rs.q(i);
+        const double diag = fma(-cg_tau, rs.q(i), cf.kjj);      // kappa_jj - dc/(M - kLf/E) [masked]   :56
         const double P = (i == 0) ? diag : fma(diag, Pm1, -(cf.ac * Pm2));
         rs.s(i) = Pm1 * fast_rcp(P);            // 1 / w_i
         Pm2 = Pm1; Pm1 = P;
@@ -550,6 +614,7 @@ struct Ctx {
       }
     }
     PHASE_MARK(5);   // back substitution
+    if (SLOW && ti == nt) set_pads(a);
   }
 };
 
@@ -561,8 +626,9 @@ constexpr size_t uniform_smem_bytes(bool fields) {
                            (QS_SMEM ? (size_t)3 * K * WB * MW : 0));
 }
 
-template <int K, int WB, int MW, int MAXR, bool QS_SMEM, bool WARPM, bool TAB>
-__global__ void __maxnreg__(MAXR) classic_uniform_kernel(const ClassicKArgs a) {
+template <int K, int WB, int MW, int MAXR, bool QS_SMEM, bool WARPM, bool TAB, bool UPAR>
+__global__ void __maxnreg__(MAXR) classic_uniform_kernel(const __grid_constant__ ClassicKArgs a) {
+  static_assert(!UPAR || TAB, "launch-uniform parameters imply uniform tables");
   static_assert(MW == 16, "warp 0 = two lanes per member (full-warp shuffles)");
   static_assert(!WARPM || (32 % WB == 0 && QS_SMEM), "member-in-warp mapping: WB bands x 32/WB members per warp");
   static_assert(WB % 2 == 0 && (WB * MW) % 32 == 0, "whole warps, even band count");
@@ -588,10 +654,12 @@ __global__ void __maxnreg__(MAXR) classic_uniform_kernel(const ClassicKArgs a) {
   const int nx = a.nx, nt = a.nt;
 
   // the TAB instance integrates the 32-member groups whose table-building parameters agree, the !TAB instance the rest
-  if (ebm_classic_group_uniform<MW>(a.par, nmem, m_first, mi) != TAB) return;
+  if constexpr (!UPAR) {
+    if (ebm_classic_group_uniform<MW>(a.par, nmem, m_first, mi) != TAB) return;
+  }
   double par[EBM_CLASSIC_NPAR];
 #pragma unroll
-  for (int k = 0; k < EBM_CLASSIC_NPAR; ++k) par[k] = a.par[(long long)k * nmem + m];
+  for (int k = 0; k < EBM_CLASSIC_NPAR; ++k) par[k] = UPAR ? a.u.par[k] : a.par[(long long)k * nmem + m];
 
   // ---- shared memory carve-up
   PhysTab* phys = reinterpret_cast<PhysTab*>(smem_raw);          // [NXP]
@@ -622,7 +690,8 @@ __global__ void __maxnreg__(MAXR) classic_uniform_kernel(const ClassicKArgs a) {
     PhysTab p; CoefTab c;
     const double lhm = (j % K == 0 || !v) ? 0.0 : a.g.lam_hi[j - 1];
     if constexpr (TAB) {
-      p.S0x = fma(-pS2, x2, pS0); p.aw = fma(-pa2, x2, pa0);
+      // pad cells: as open water they absorb aw S = 1000 W/m^2 and stay warm, as ice ai S ~ 0 and they stay frozen
+      p.S0x = v ? fma(-pS2, x2, pS0) : 1e-3; p.aw = v ? fma(-pa2, x2, pa0) : 1e6;
       c.kjj = fma(fac, ll + lh, one_dttau); c.aoff = -fac * ll; c.coff = -fac * lh; c.ac = c.aoff * (-fac * lhm);
     } else {   // geometry only: Ctx::phys_at / coef_at apply the member's parameters
       p.S0x = x2; p.aw = x2;
@@ -660,15 +729,16 @@ __global__ void __maxnreg__(MAXR) classic_uniform_kernel(const ClassicKArgs a) {
     bandc[2 * b] = be; bandc[2 * b + 1] = ga;
   }
 
-  Ctx<K, WB, MW, QS_SMEM, WARPM, TAB> cx;
+  Ctx<K, WB, MW, QS_SMEM, WARPM, TAB, UPAR> cx;
   cx.S0m = pS0; cx.S2m = pS2; cx.a0m = pa0; cx.a2m = pa2; cx.facm = fac; cx.fac2m = fac * fac; cx.one_dttaum = one_dttau;
   cx.rs.base = qsm + tid;
   cx.rs.stride = WB * MW;
   cx.phys = phys; cx.elim = elim; cx.coef = coef; cx.bandc = bandc;
   cx.iface = iface; cx.zs = zs; cx.red = red; cx.sumE = sumE; cx.sumT = sumT; cx.sumH = sumH;
-  cx.A = pA; cx.Fb = pFb; cx.ai = pai; cx.cg_tau = cg_tau; cx.M = pB + cg_tau; cx.kLf = pk * pLf;
-  cx.inv_cw = 1.0 / pcw; cx.dt = dt; cx.dt_tau = dt_tau; cx.dttau_cw = dt_tau * cx.inv_cw; cx.dc = dt_tau * cg_tau;
-  cx.inv_nt = 1.0 / nt; cx.inv_Lf = 1.0 / pLf;
+  cx.A_ = pA; cx.Fb_ = pFb; cx.ai_ = pai; cx.cg_tau_ = cg_tau; cx.M_ = pB + cg_tau; cx.kLf_ = pk * pLf;
+  cx.inv_cw_ = 1.0 / pcw; cx.dt_ = dt; cx.dt_tau_ = dt_tau; cx.dttau_cw_ = dt_tau * cx.inv_cw_; cx.dc_ = dt_tau * cg_tau;
+  cx.inv_nt_ = 1.0 / nt; cx.inv_Lf_ = 1.0 / pLf;
+  const double cM = UPAR ? a.u.M : cx.M_, ckLf = UPAR ? a.u.kLf : cx.kLf_;
   cx.band = band; cx.mi = mi; cx.j0 = band * K;
   cx.solver = WARPM ? false : ((a.dbg & 8) ? warp == 0 : (wrot == (NWARP > 1 ? 1 : 0)));
   cx.active = active;
@@ -685,9 +755,10 @@ __global__ void __maxnreg__(MAXR) classic_uniform_kernel(const ClassicKArgs a) {
     cx.E[i] = (v ? a.E[(long long)j * nmem + m] : 1.0) + 0.0;     // pad cells: decoupled open-water rows
     cx.Tg[i] = v ? a.Tg[(long long)j * nmem + m] : 0.0;
     sumE[cx.cidx(i)] = 0.0;
-    cx.rs.r(i) = cx.E[i] * fast_rcp(fma(cx.M, cx.E[i], -cx.kLf));   // same expression as in the step: r is a pure function of E
+    cx.rs.r(i) = cx.E[i] * fast_rcp(fma(cM, cx.E[i], -ckLf));   // same expression as in the step: r is a pure function of E
     if (cx.cta_fields) { sumT[cx.cidx(i)] = 0.0; sumH[cx.cidx(i)] = 0.0; }
   }
+  cx.set_pads(a);
   // Forcing{true}: base == peak == cool, all breakpoints 0 -> the call is the constant `base`
   const double fbase = fr[0 * MW + mi];
   const bool myconst = fr[1 * MW + mi] == fbase && fr[2 * MW + mi] == fbase && fr[6 * MW + mi] == 0.0 &&
@@ -695,12 +766,13 @@ __global__ void __maxnreg__(MAXR) classic_uniform_kernel(const ClassicKArgs a) {
   const bool constf = __syncthreads_and(myconst) != 0;
   const bool has_raw = __syncthreads_or(cx.sel && (a.raw != nullptr)) != 0;
 
-  double S1c_next = pS1 * __ldg(a.g.ctab);   // S1*cos(2*pi*t_1); ctab[nt] == ctab[0] closes the year (classic.jl:25)
+  const double cS1 = UPAR ? a.u.par[5] : pS1;
+  double S1c_next = cS1 * __ldg(a.g.ctab);   // S1*cos(2*pi*t_1); ctab[nt] == ctab[0] closes the year (classic.jl:25)
   for (int year = a.year0; year < a.year0 + a.nyears; ++year) {
     const bool raw_year = has_raw && (!a.lastonly || year == a.dur - 1);
     for (int ti = 1; ti <= nt; ++ti) {
       // column i+1 of this step is column i of the next: one table load per step, consumed late in the step
-      const double S1c0 = S1c_next, S1c1 = pS1 * __ldg(a.g.ctab + ti);
+      const double S1c0 = S1c_next, S1c1 = cS1 * __ldg(a.g.ctab + ti);
       S1c_next = S1c1;
       double f = fbase;
       if (!constf) {
@@ -728,7 +800,7 @@ __global__ void __maxnreg__(MAXR) classic_uniform_kernel(const ClassicKArgs a) {
   if (bad && a.flags != nullptr) atomicOr(a.flags + mo, 1);
 }
 
-template <int K, int WB, int MW, int MAXR, bool QS_SMEM = false, bool WARPM = false, bool TAB = true>
+template <int K, int WB, int MW, int MAXR, bool QS_SMEM = false, bool WARPM = false, bool TAB = true, bool UPAR = false>
 int launch_uniform(const ClassicKArgs& a, cudaStream_t stream) {
   if (a.nx > K * WB) {
     ebm_set_error("classic_uniform: nx=%d exceeds %d bands of %d cells", a.nx, WB, K);
@@ -736,7 +808,7 @@ int launch_uniform(const ClassicKArgs& a, cudaStream_t stream) {
   }
   const bool fields = a.seasonal != nullptr && a.field_stride > 0;
   const size_t smem = uniform_smem_bytes<K, WB, MW, QS_SMEM>(fields);
-  auto kern = classic_uniform_kernel<K, WB, MW, MAXR, QS_SMEM, WARPM, TAB>;
+  auto kern = classic_uniform_kernel<K, WB, MW, MAXR, QS_SMEM, WARPM, TAB, UPAR>;
   EBM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // leave room for several CTAs per SM: ask for the largest shared-memory carve-out (L1 is hardly used)
   EBM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -756,7 +828,11 @@ int ebm_classic_uniform_max_nx() { return 208; }   // 8 bands of 13 cells up to 
 int ebm_classic_uniform_slots() {
   int dev = 0, sms = 0, per_sm = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) { cudaGetLastError(); return 0; }
-  auto kern = classic_uniform_kernel<13, 8, 16, 168, true, false, true>;
+#ifdef EBM_DEV_FAST_BUILD
+  auto kern = classic_uniform_kernel<13, 8, 16, 168, true, false, true, true>;
+#else
+  auto kern = classic_uniform_kernel<13, 8, 16, 168, true, false, true, false>;
+#endif
   const size_t smem = uniform_smem_bytes<13, 8, 16, true>(false);
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -768,8 +844,13 @@ int ebm_classic_uniform_slots() {
 // applied per member, every band eliminated in full
 int ebm_launch_classic_general(const ClassicKArgs& a, cudaStream_t stream) {
   if (a.nx > ebm_classic_uniform_max_nx()) return EBM_OK;
+  if (a.upar && a.nx <= 104) return EBM_OK;   // the launch-uniform instance integrated every group
+#ifdef EBM_DEV_FAST_BUILD
+  return EBM_OK;
+#else
   if (a.nx > 104) return launch_uniform<13, 16, 16, 255, true, false, false>(a, stream);
   return launch_uniform<13, 8, 16, 168, true, false, false>(a, stream);
+#endif
 }
 
 // dev: read and reset the phase counters (zeros unless built with -DEBM_PHASE_TIMING)
@@ -788,6 +869,9 @@ extern "C" int ebm_debug_phase_cycles(unsigned long long* out64) {
 // variant: 0 = default.  Other values select alternative instantiations for tuning (env EBM_CLASSIC_VARIANT).
 int ebm_launch_classic_uniform(const ClassicKArgs& a, int variant, cudaStream_t stream) {
   if (a.nx > ebm_classic_uniform_max_nx()) return EBM_OK;   // larger grids: the band kernel integrates every group
+#ifdef EBM_DEV_FAST_BUILD   // dev: only the launch-uniform instance (compile time)
+  return launch_uniform<13, 8, 16, 168, true, false, true, true>(a, stream);
+#else
   if (a.nx > 104) return launch_uniform<13, 16, 16, 255, true>(a, stream);   // 16 bands, 8 warps per CTA, 1 CTA per SM
   switch (variant) {
     // <K cells/thread, WB bands, MW members/CTA, max registers/thread, band rows in smem, member-in-warp mapping>
@@ -798,6 +882,9 @@ int ebm_launch_classic_uniform(const ClassicKArgs& a, int variant, cudaStream_t 
     case 9: return launch_uniform<13, 8, 16, 168, true, true>(a, stream);   // member-in-warp, no CTA barrier:   717 k
     // default: band rows (pivots / spikes / carried reciprocals) in thread-private shared memory, 168 registers,
     // 3 CTAs (12 warps) per SM: 921 k
-    default: return launch_uniform<13, 8, 16, 168, true>(a, stream);
+    default:
+      if (a.upar) return launch_uniform<13, 8, 16, 168, true, false, true, true>(a, stream);
+      return launch_uniform<13, 8, 16, 168, true>(a, stream);
   }
+#endif
 }

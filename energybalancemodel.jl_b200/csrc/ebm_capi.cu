@@ -306,6 +306,31 @@ extern "C" int32_t ebm_classic_run_device(const ebm_grid_t* grid, const ebm_clas
   a.dbg = getenv("EBM_DBG") ? atoi(getenv("EBM_DBG")) : 0;
   const int ypl = opt.years_per_launch > 0 ? opt.years_per_launch : grid->dur;
   static const int variant = getenv("EBM_CLASSIC_VARIANT") ? atoi(getenv("EBM_CLASSIC_VARIANT")) : 0;
+  // ---- launch-uniform parameters (a forcing sweep such as C4: members differ in forcing and initial state only).  The
+  // member constants then travel in the kernel argument block and are constant-bank operands of the FP64 instructions;
+  // the 26 registers they otherwise occupy go to instruction-level parallelism (classic_uniform.cu, UPAR).  The host
+  // derives them with the same IEEE expressions the kernels evaluate per member, so the results are bit-identical.
+  DevBufs upar_bufs;
+  if (!opt.strict && variant == 0 && a.nx <= 104 && !getenv("EBM_NO_UPAR")) {
+    double* dhead = nullptr; int* ddiff = nullptr;
+    EBM_TRY(upar_bufs.alloc(&dhead, EBM_CLASSIC_NPAR));
+    EBM_TRY(upar_bufs.alloc(&ddiff, 1));
+    EBM_TRY(ebm_launch_par_uniform(a.par, EBM_CLASSIC_NPAR, a.nmem, dhead, ddiff, stream));
+    int differs = 1;
+    EBM_CUDA_TRY(cudaMemcpyAsync(&differs, ddiff, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    EBM_CUDA_TRY(cudaMemcpyAsync(a.u.par, dhead, sizeof(double) * EBM_CLASSIC_NPAR, cudaMemcpyDeviceToHost, stream));
+    EBM_CUDA_TRY(cudaStreamSynchronize(stream));
+    if (!differs) {
+      const double* p = a.u.par;   // D A B cw S0 S1 S2 a0 a2 ai Fb k Lf cg tau
+      ClassicUPar& u = a.u;
+      u.dt = 1.0 / a.nt;
+      u.cg_tau = p[13] / p[14]; u.dt_tau = u.dt / p[14];
+      u.A = p[1]; u.Fb = p[10]; u.ai = p[9]; u.M = p[2] + u.cg_tau; u.kLf = p[11] * p[12];
+      u.inv_cw = 1.0 / p[3]; u.dttau_cw = u.dt_tau * u.inv_cw; u.dc = u.dt_tau * u.cg_tau;
+      u.inv_nt = 1.0 / a.nt; u.inv_Lf = 1.0 / p[12];
+      a.upar = 1;
+    }
+  }
   // ---- wave balancing.  A CTA integrates 16 members for the whole run; the device holds `slots` CTAs at a time.
   // 8192 members (the 8-GPU share of the 65 536-member sweep) are 512 CTAs on 444 slots: one launch runs them as
   // two waves, the second 15 % full.  Cut instead into 8 ranges of CTAs on 8 streams, each advancing in chunks of

@@ -53,6 +53,13 @@ struct EbmGridTables {
 };
 
 // ----------------------------------------------------------------------------- kernel argument blocks
+// Classic member constants of a launch in which every member has the same 15 parameters (the C4 forcing sweep):
+// derived on the host with the same IEEE expressions the kernels use per member, read as constant-bank operands.
+struct ClassicUPar {
+  double par[EBM_CLASSIC_NPAR];
+  double A, Fb, ai, cg_tau, M, kLf, inv_cw, dt, dt_tau, dttau_cw, dc, inv_nt, inv_Lf;
+};
+
 struct ClassicKArgs {
   int nx, nt, dur, W;
   long long nmem;
@@ -67,6 +74,8 @@ struct ClassicKArgs {
   double* diag; double* seasonal; double* raw; int* flags;
   const long long* orig;         // NULL or [nmem]: original member index of slot m (output rows, field selection)
   int dbg;                       // development switches (env EBM_DBG)
+  int upar;                      // 1: u is valid (every member of the launch shares all 15 parameters)
+  ClassicUPar u;
   long long block0, nblocks;     // classic_uniform.cu: this launch covers the 16-member groups [block0, block0 + nblocks); nblocks 0 = all
 };
 
@@ -106,6 +115,8 @@ int ebm_launch_miz_single_step(const EbmGridTables& g, const double* par22, int 
                                double* vars_out, long long* iters, cudaStream_t stream);
 int ebm_launch_transpose(const double* src, double* dst, long long rows, long long cols, cudaStream_t stream);
 int ebm_launch_fill(double* dst, long long n, double v, cudaStream_t stream);
+// head[k] = par[k][0] (k < npar); *differs = 1 if some member's parameters are not bit-identical to member 0's
+int ebm_launch_par_uniform(const double* par, int npar, long long nmem, double* head, int* differs, cudaStream_t stream);
 // dst[c][r] = src[idx[r]][c] (rows x cols -> cols x rows with a row gather); inverse: dst[idx[r]][c] = src[c][r]
 int ebm_launch_gather_transpose(const double* src, double* dst, long long rows, long long cols, const long long* idx,
                                 int inverse, cudaStream_t stream);

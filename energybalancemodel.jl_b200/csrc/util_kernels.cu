@@ -1,5 +1,6 @@
 // util_kernels.cu -- layout helpers and the FP64 roof microbenchmark.
 #include "ebm_internal.cuh"
+#include <algorithm>
 
 namespace {
 
@@ -98,6 +99,29 @@ int ebm_launch_scatter_rows(const double* src, double* dst, long long nrows, lon
 int ebm_launch_fill(double* dst, long long n, double v, cudaStream_t stream) {
   if (n <= 0) return EBM_OK;
   fill_kernel<<<1184, 256, 0, stream>>>(dst, n, v);
+  EBM_CUDA_TRY(cudaGetLastError());
+  ebm_count_launch();
+  return EBM_OK;
+}
+
+// head[k] = par[k][0]; *differs |= 1 when any member's parameter k is not bit-identical to member 0's
+__global__ void par_uniform_kernel(const double* __restrict__ par, int npar, long long nmem, double* __restrict__ head,
+                                   int* __restrict__ differs) {
+  bool diff = false;
+  for (int k = 0; k < npar; ++k) {
+    const double* row = par + (long long)k * nmem;
+    const long long ref = __double_as_longlong(row[0]);
+    if (blockIdx.x == 0 && threadIdx.x == 0) head[k] = row[0];
+    for (long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x; m < nmem; m += (long long)gridDim.x * blockDim.x)
+      diff = diff || (__double_as_longlong(row[m]) != ref);
+  }
+  if (__syncthreads_or(diff) && threadIdx.x == 0) atomicOr(differs, 1);
+}
+
+int ebm_launch_par_uniform(const double* par, int npar, long long nmem, double* head, int* differs, cudaStream_t stream) {
+  EBM_CUDA_TRY(cudaMemsetAsync(differs, 0, sizeof(int), stream));
+  const int blocks = (int)std::min<long long>(592, (nmem + 255) / 256);
+  par_uniform_kernel<<<blocks, 256, 0, stream>>>(par, npar, nmem, head, differs);
   EBM_CUDA_TRY(cudaGetLastError());
   ebm_count_launch();
   return EBM_OK;
