@@ -39,6 +39,9 @@ namespace {
 constexpr double kPi = 3.141592653589793;   // Float64(pi)
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kWarps = 4;                   // members per CTA
+#ifndef EBM_MIZ_GC
+#define EBM_MIZ_GC 3
+#endif
 
 __device__ __forceinline__ double shfl_up1(double v) { return __shfl_up_sync(kFull, v, 1); }
 __device__ __forceinline__ double shfl_dn1(double v) { return __shfl_down_sync(kFull, v, 1); }
@@ -53,15 +56,21 @@ __device__ __forceinline__ double warp_min(double v) {
   return v;
 }
 
-// reciprocal of an ordinary number (normal, 2^-1000 < |y| < 2^1000): ~1 ulp, no slow path
+// reciprocal of an ordinary number (normal, 2^-1000 < |y| < 2^1000): ~1 ulp, no slow path.  The MUFU.RCP64H seed is
+// good to 2^-20 (measured, profiles/r2_microbench.txt): one cubic step (3 FMA) reaches 1 ulp
 __device__ __forceinline__ double rcp_nr(double y) {
   double r;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(y));
+#ifdef EBM_MIZ_RCP_NEWTON2
   double e = fma(-y, r, 1.0);
   r = fma(r, e, r);
   e = fma(-y, r, 1.0);
   r = fma(r, e, r);
   return r;
+#else
+  const double e = fma(-y, r, 1.0);
+  return fma(r, fma(e, e, e), r);
+#endif
 }
 // c ? a : b as one SELP with both operands evaluated: the compiler otherwise branches around "expensive" operands,
 // which splits the unrolled per-cell code into scheduling regions and serialises the K cells of a lane
@@ -89,7 +98,7 @@ __device__ __forceinline__ double sel1(bool c, double b) {
 }
 #endif
 // zero / sign tests on the integer pipe (the FP64 pipe is the bottleneck); +0 and -0 are both zero
-__device__ __forceinline__ bool is_zero(double v) { return ((__double2hiint(v) << 1) | __double2loint(v)) == 0; }
+__device__ __forceinline__ bool is_zero(double v) { return ((__double2hiint(v) & 0x7fffffff) | __double2loint(v)) == 0; }   // one LOP3 with predicate output
 // x / y with y an ordinary non-zero number (no denormal / huge denominators: DESIGN.md 4.3)
 __device__ __forceinline__ double div_n(double x, double y) { return x * rcp_nr(y); }
 // x / y with y zero or ordinary: IEEE results for y == +-0 (x/0 = +-Inf, 0/0 = NaN/0 = NaN), branch free
@@ -138,21 +147,27 @@ __device__ __forceinline__ void diffuse(const double* __restrict__ lo, const dou
 template <int K, class RowFn>
 __device__ __forceinline__ void tridiag(int lane, RowFn row, double (&rhs)[K]) {
   // local forward elimination:  x_i + q_i x_{i+1} + s_i xL = y_i   (xL = last unknown of the previous lane)
+  // Pivots in determinant form: P_i = w_0 ... w_i obeys P_i = d_i P_{i-1} - (l_i u_{i-1}) P_{i-2} -- one dependent FMA
+  // per row instead of FMA -> reciprocal -> product (the K reciprocals 1/w_i = P_{i-1}/P_i are then independent of
+  // each other; |w| <= 2 D / dx^2 + k/hmin + B ~ 1e5, so P stays far inside the double range for K <= 8)
   double q[K], s[K];
   {
-    double qp = 0.0, yp = 0.0, sp = 0.0;
+    double Pm2 = 1.0, Pm1 = 1.0, jup = 0.0;
 #pragma unroll
     for (int i = 0; i < K; ++i) {
       double jl_i, jd_i, ju_i;
       row(i, jl_i, jd_i, ju_i);
-      const double w = (i == 0) ? jd_i : fma(-jl_i, qp, jd_i);
-      const double iw = rcp_nr(w);
-      const double tq = jl_i * iw;
+      const double P = (i == 0) ? jd_i : fma(jd_i, Pm1, -((jl_i * jup) * Pm2));
+      const double iw = Pm1 * rcp_nr(P);
+      s[i] = jl_i * iw;                       // tq_i, turned into the spike below
       q[i] = ju_i * iw;
-      const double yi = (i == 0) ? rhs[i] * iw : fma(-tq, yp, rhs[i] * iw);
-      const double si = (i == 0) ? tq : -tq * sp;
-      s[i] = si; rhs[i] = yi;
-      qp = q[i]; yp = yi; sp = si;
+      rhs[i] = rhs[i] * iw;
+      Pm2 = Pm1; Pm1 = P; jup = ju_i;
+    }
+#pragma unroll
+    for (int i = 1; i < K; ++i) {
+      rhs[i] = fma(-s[i], rhs[i - 1], rhs[i]);
+      s[i] = -s[i] * s[i - 1];
     }
   }
   // reduce row 0 to  x_0 = al - be*xL - ga*z   (z = my last unknown)
@@ -431,79 +446,96 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) miz_fast_kernel(const MizKA
       // two instantiations: the hot one (no sampling this step, no field output) is straight-line code
       auto cells = [&](auto slow_tag) {
       constexpr bool SLOW = decltype(slow_tag)::value;
+      constexpr int GC = (K % EBM_MIZ_GC == 0) ? EBM_MIZ_GC : 2;   // cells per statement-major group (K is even)
+      // ptxas keeps the source order to a large extent and a warp issues in order: written cell after cell, the six
+      // ~100-instruction dependent chains of a lane run one after the other (static schedule: 2.6 issue cycles per FP64
+      // instruction).  Statement-major over groups of GC cells -- every statement for the group's cells before the
+      // next statement -- gives the warp GC independent chains; the arithmetic of every cell is unchanged.
 #pragma unroll
-      for (int i = 0; i < K; ++i) {
-        const int sidx = i * 32 + lane;
-        const double xj = tabs.x[sidx], x2j = tabs.x2[sidx];
-        const double Eio = EI(i), Ewo = EW(i), ho = HH(i), Do = DD(i), pho = phi[i];
-        const double om = 1 - pho;
-        const bool noD = is_zero(Do), noh = is_zero(ho), one = pho == 1.0;
-        const double S = fma(-CST(S2), x2j, fma(-S1c, xj, CST(S0)));
-        const double common = fma(-CST(B), tb[i], dif[i]) + CST(cBF);                    // -(A + B(Tb-Tm)) + diffusion + Fb (+ fA below)
-        const double Fvi = c0[i] + common;                                            // :99-100 (ice)
-        const double Fvw = fma(fma(-CST(a2), x2j, CST(a0)), S, fA) + common;                  // (water)
-        const double wl = fma(CST(m1), TW(i), CST(c_wl0));                                      // :71
-        const double rD = rcp_nr(sel1(noD, Do));
-        const double an = sel0(noD, pho * (rD * rD));                              // alpha * n
-        const double n = an * CST(inv_alpha);                                            // num :84-85
-        const double Flat = sel0(noD, (pho * ho) * (wl * CST(c_flat)) * rD);              // :104-105
-        const double rEi = fma(fma(pho, Fvi, Flat), dt, Eio);                         // :137,148,166
-        const double rEw = fma(fma(om, Fvw, -Flat), dt, Ewo);                         // :138,148,167
-        const double cEi = rEi > 0.0 ? 0.0 : rEi, cEw = rEw < 0.0 ? 0.0 : rEw;        // redistributeE :110-111
-        const double psiEw_dt = rEw - cEw;
-        double Ei_n = cEi + psiEw_dt;
-        const double Ew_n = cEw + (rEi - cEi);
-        const double ring = an * fma(CST(c_r1), Do, CST(c_r2));                          // area_lead :91
-        const double Al = (ring < om) ? ring : om;                                    // :92
-        const double psiEw = psiEw_dt * ntd;                                          // psiEwdt / dt (:173)
-        const double Ql = sel0(one, Al * ROM(i) * psiEw);            // split_psiEw :121-122
-        const double Qp = psiEw - Ql;
-        const double dn = -Qp * CST(c_dn);                                                 // :127,174
-        const double lat_grow = sel0(noh, div_z(-Do, sel1(noh, CST(twoLf) * ho * pho)) * Ql);   // :142,144
-        const double Dt = fma(CST(c_melt), wl, lat_grow) + CST(c_weld) * pho * (Do * Do * Do);  // :141-145
-        const double rDn = fma(Dt, dt, Do);                                           // :175
-        const double total = n + dn;
-        const bool tz = is_zero(total);
-        const double rt = rcp_nr(sel1(tz, total));
-        double Dn = sel0(tz, fma(n, rDn, dn * CST(Dmin)) * rt);                          // average :131-132
-        Dn = Dn > CST(Dmax) ? CST(Dmax) : (Dn < CST(Dmin) ? CST(Dmin) : Dn);                          // :177
-        Dn = sel0(is_zero(Ei_n), Dn);                                                  // :178
-        double rh = fma(-Fvi, CST(dt_Lf), ho);                                             // :139,179
-        rh = rh < 0.0 ? 0.0 : rh;                                                     // :180
-        const double hn = sel0(tz, fma(n, rh, dn * CST(hmin)) * rt);                     // :181
-        const bool hz = is_zero(hn);
-        const double r_hn = rcp_nr(sel1(hz, hn));
-        RHP(i) = sel(hz, CST(inv_hmin), r_hn);                                           // next step's 1/hp (:51)
-        double ph = sel0(hz, -Ei_n * r_hn * CST(inv_Lf));                              // concentration :75-76
-        if (ph > 1.0) ph = 1.0;                                                       // :77
-        Ei_n = sel0(hz, Ei_n);                                                          // :185
-        const double omn = 1 - ph;
-        const double En = fma(ph, Ei_n, omn * Ew_n);                                  // :186
-        const double Tn = fma(Ti[i], ph, omn * TW(i));                                // :187
-        EI(i) = Ei_n; EW(i) = Ew_n; DD(i) = Dn; HH(i) = hn; phi[i] = ph;
+      for (int g0 = 0; g0 < K; g0 += GC) {
+        constexpr int G = GC;
+#define FORG _Pragma("unroll") for (int g = 0; g < G; ++g)
+#define I (g0 + g)
+        double xj[G], x2j[G], Eio[G], Ewo[G], ho[G], Do[G], pho[G], om[G], S[G], common[G], Fvi[G], Fvw[G], wl[G], rD[G];
+        double an[G], n[G], Flat[G], rEi[G], rEw[G], cEi[G], cEw[G], psiEw_dt[G], Ei_n[G], Ew_n[G], ring[G], Al[G];
+        double psiEw[G], Ql[G], dn[G], lat_grow[G], Dt[G], rDn[G], total[G], rt[G], Dn[G], rh[G], hn[G], r_hn[G], ph[G];
+        double omn[G], En[G], Tn[G], tw[G];
+        bool noD[G], noh[G], one[G], tz[G], hz[G];
+        FORG { const int sidx = I * 32 + lane; xj[g] = tabs.x[sidx]; x2j[g] = tabs.x2[sidx]; }
+        FORG { Eio[g] = EI(I); Ewo[g] = EW(I); ho[g] = HH(I); Do[g] = DD(I); pho[g] = phi[I]; tw[g] = TW(I); }
+        FORG om[g] = 1 - pho[g];
+        FORG { noD[g] = is_zero(Do[g]); noh[g] = is_zero(ho[g]); one[g] = pho[g] == 1.0; }
+        FORG S[g] = fma(-CST(S2), x2j[g], fma(-S1c, xj[g], CST(S0)));
+        FORG common[g] = fma(-CST(B), tb[I], dif[I]) + CST(cBF);                       // -(A + B(Tb-Tm)) + diffusion + Fb (+ fA below)
+        FORG Fvi[g] = c0[I] + common[g];                                               // :99-100 (ice)
+        FORG Fvw[g] = fma(fma(-CST(a2), x2j[g], CST(a0)), S[g], fA) + common[g];       // (water)
+        FORG wl[g] = fma(CST(m1), tw[g], CST(c_wl0));                                  // :71
+        FORG rD[g] = rcp_nr(sel1(noD[g], Do[g]));
+        FORG an[g] = sel0(noD[g], pho[g] * (rD[g] * rD[g]));                           // alpha * n
+        FORG n[g] = an[g] * CST(inv_alpha);                                            // num :84-85
+        FORG Flat[g] = sel0(noD[g], (pho[g] * ho[g]) * (wl[g] * CST(c_flat)) * rD[g]); // :104-105
+        FORG rEi[g] = fma(fma(pho[g], Fvi[g], Flat[g]), dt, Eio[g]);                   // :137,148,166
+        FORG rEw[g] = fma(fma(om[g], Fvw[g], -Flat[g]), dt, Ewo[g]);                   // :138,148,167
+        FORG { cEi[g] = rEi[g] > 0.0 ? 0.0 : rEi[g]; cEw[g] = rEw[g] < 0.0 ? 0.0 : rEw[g]; }   // redistributeE :110-111
+        FORG psiEw_dt[g] = rEw[g] - cEw[g];
+        FORG Ei_n[g] = cEi[g] + psiEw_dt[g];
+        FORG Ew_n[g] = cEw[g] + (rEi[g] - cEi[g]);
+        FORG ring[g] = an[g] * fma(CST(c_r1), Do[g], CST(c_r2));                       // area_lead :91
+        FORG Al[g] = (ring[g] < om[g]) ? ring[g] : om[g];                              // :92
+        FORG psiEw[g] = psiEw_dt[g] * ntd;                                             // psiEwdt / dt (:173)
+        FORG Ql[g] = sel0(one[g], Al[g] * ROM(I) * psiEw[g]);                          // split_psiEw :121-122
+        FORG dn[g] = -(psiEw[g] - Ql[g]) * CST(c_dn);                                  // :127,174
+        FORG lat_grow[g] = sel0(noh[g], div_z(-Do[g], sel1(noh[g], CST(twoLf) * ho[g] * pho[g])) * Ql[g]);   // :142,144
+        FORG Dt[g] = fma(CST(c_melt), wl[g], lat_grow[g]) + CST(c_weld) * pho[g] * (Do[g] * Do[g] * Do[g]);  // :141-145
+        FORG rDn[g] = fma(Dt[g], dt, Do[g]);                                           // :175
+        FORG total[g] = n[g] + dn[g];
+        FORG tz[g] = is_zero(total[g]);
+        FORG rt[g] = rcp_nr(sel1(tz[g], total[g]));
+        FORG Dn[g] = sel0(tz[g], fma(n[g], rDn[g], dn[g] * CST(Dmin)) * rt[g]);        // average :131-132
+        FORG Dn[g] = sel(Dn[g] > CST(Dmax), CST(Dmax), sel(Dn[g] < CST(Dmin), CST(Dmin), Dn[g]));   // clamp (NaN stays NaN) :177
+        FORG Dn[g] = sel0(is_zero(Ei_n[g]), Dn[g]);                                    // :178
+        FORG rh[g] = fma(-Fvi[g], CST(dt_Lf), ho[g]);                                  // :139,179
+        FORG rh[g] = rh[g] < 0.0 ? 0.0 : rh[g];                                        // :180
+        FORG hn[g] = sel0(tz[g], fma(n[g], rh[g], dn[g] * CST(hmin)) * rt[g]);         // :181
+        FORG hz[g] = is_zero(hn[g]);
+        FORG r_hn[g] = rcp_nr(sel1(hz[g], hn[g]));
+        FORG RHP(I) = sel(hz[g], CST(inv_hmin), r_hn[g]);                              // next step's 1/hp (:51)
+        FORG ph[g] = sel0(hz[g], -Ei_n[g] * r_hn[g] * CST(inv_Lf));                    // concentration :75-76
+        FORG { if (ph[g] > 1.0) ph[g] = 1.0; }                                         // :77
+        FORG Ei_n[g] = sel0(hz[g], Ei_n[g]);                                           // :185
+        FORG omn[g] = 1 - ph[g];
+        FORG En[g] = fma(ph[g], Ei_n[g], omn[g] * Ew_n[g]);                            // :186
+        FORG Tn[g] = fma(Ti[I], ph[g], omn[g] * tw[g]);                                // :187
+        FORG { EI(I) = Ei_n[g]; EW(I) = Ew_n[g]; DD(I) = Dn[g]; HH(I) = hn[g]; phi[I] = ph[g]; }
 
         // ---- sampling
+        FORG {
+        const int i = I;
+        const int sidx = i * 32 + lane;
         const bool real = lane * K + i < nx;
         const double wj = tabs.wts[sidx];
-        accT = fma(wj, Tn, accT); accE = fma(wj, En, accE); accP = fma(wj, ph, accP);
-        icebits |= (unsigned)(ph > 0.0 && real) << i;
+        accT = fma(wj, Tn[g], accT); accE = fma(wj, En[g], accE); accP = fma(wj, ph[g], accP);
+        icebits |= (unsigned)(ph[g] > 0.0 && real) << i;
         if (SLOW) {
         if (season == 0 || season == 1) {
-          dgT = fma(wj, Tn, dgT); dgE = fma(wj, En, dgE); dgP = fma(wj, ph, dgP);
-          if (ph > 0.0 && real) dgX = fmin(dgX, xj);
+          dgT = fma(wj, Tn[g], dgT); dgE = fma(wj, En[g], dgE); dgP = fma(wj, ph[g], dgP);
+          if (ph[g] > 0.0 && real) dgX = fmin(dgX, xj[g]);
         } else if (season == 2) {
-          if (((icebits >> i) & 1u) != 0u) dgX = fmin(dgX, xj);
+          if (((icebits >> i) & 1u) != 0u) dgX = fmin(dgX, xj[g]);
         }
         if (sel_m && real) {
           double v[EBM_MIZ_NVAR];
-          v[EBM_MV_T] = Tn; v[EBM_MV_Ei] = Ei_n;
-          v[EBM_MV_Ti] = is_zero(Ei_n) ? NAN : Ti[i];                                 // :193
-          v[EBM_MV_D] = Dn; v[EBM_MV_n] = n; v[EBM_MV_h] = hn; v[EBM_MV_phi] = ph;
-          v[EBM_MV_E] = En; v[EBM_MV_Ew] = Ew_n;
-          v[EBM_MV_Tw] = (ph > 0.99) ? NAN : TW(i);                                   // :194
+          v[EBM_MV_T] = Tn[g]; v[EBM_MV_Ei] = Ei_n[g];
+          v[EBM_MV_Ti] = is_zero(Ei_n[g]) ? NAN : Ti[i];                              // :193
+          v[EBM_MV_D] = Dn[g]; v[EBM_MV_n] = n[g]; v[EBM_MV_h] = hn[g]; v[EBM_MV_phi] = ph[g];
+          v[EBM_MV_E] = En[g]; v[EBM_MV_Ew] = Ew_n[g];
+          v[EBM_MV_Tw] = (ph[g] > 0.99) ? NAN : tw[g];                                // :194
           store_cell(a, lane * K + i, msel, year, ti, season, v);
         }
         }   // SLOW
+        }
+#undef FORG
+#undef I
       }
       };    // cells
       if (sel_m || season >= 0) cells(std::true_type{}); else cells(std::false_type{});

