@@ -366,9 +366,14 @@ struct Ctx {
     double dgT = 0.0, dgE = 0.0, dgA = 0.0, dgX = 2.0;
 
     // ---- physics (classic.jl:47-53) and the rows of the implicit system (:55-63)
-    bool has_ice = false;
+    // One code path per warp (a warp whose lanes disagree would run both, one after the other): the open-water code
+    // below only if no lane holds an ice cell or a cell about to freeze (E < 1/4: signed compare of the high words --
+    // |dE| per step is ~dt * 300), else the ice code for every lane.  Both give the same bits for an open-water cell
+    // that stays open water, so the result does not depend on which members share a warp.
+    int hmin = 0x7fffffff;
 #pragma unroll
-    for (int i = 0; i < K; ++i) has_ice = has_ice || is_neg(E[i]);
+    for (int i = 0; i < K; ++i) hmin = min(hmin, __double2hiint(E[i]));
+    const bool has_ice = __any_sync(0xffffffffu, hmin < 0x3fd00000);
     if (!has_ice) {
       bool crossed = false;
       double se[K];                                         // annual sums: loaded up front, stored after the loop, so
@@ -380,9 +385,9 @@ struct Ctx {
         const double S = fma(-S1c0, p.S1x, p.S0x);          // S[j,i]; S1x holds x_j, S0x = S0 - S2 x_j^2
         const double Eo = E[i], Tgo = Tg[i];
         const double alpha = is_zero(Eo) ? 0.0 : p.aw;      // alpha = aw, or 0 at E == 0                 :47
-        const double Cb = fma(alpha, S, fma(cg_tau, Tgo, fmAFb));   // C + Fb                             :48
+        const double C = fma(alpha, S, fma(cg_tau, Tgo, fmA));                                    //     :48
         const double T = Eo * inv_cw;                                                             //     :51
-        const double En = fma(dt, fma(-M, T, Cb), Eo);                                            //     :53
+        const double En = fma(dt, fma(-M, T, C) + Fb, Eo);          // (operation order of ice_group)   :53
         E[i] = En;
         Tg[i] = fma(dttau_cw, En, Tgo);
         if constexpr (!TAB) rs.q(i) = 0.0;
@@ -391,7 +396,7 @@ struct Ctx {
       }
 #pragma unroll
       for (int i = 0; i < K; ++i) sumE[cidx(i)] = se[i];
-      if (crossed) {                                        // freeze-up inside this step (rare): literal mask
+      if (crossed) {   // freeze-up of a cell with E >= 1/4 inside one step (never at the reference's step sizes): literal mask
 #pragma unroll
         for (int i = 0; i < K; ++i) rs.q(i) = 0.0;
 #pragma unroll
