@@ -389,8 +389,9 @@ def device_pass(env, workload, nmem_total, years, steps, warmup, sample_clocks=F
 
 def roofline_record(env, workload, res, traffic):
     frac = res["achieved_tflops"] / env.peak_tf
-    kernel = ("classic_uniform_kernel<13,8,16,168> (parameter-uniform 32-member groups; its per-member-coefficient instance "
-              "takes the rest)" if workload == "classic" else "miz_fast_kernel<6>")
+    kernel = ("classic_uniform_kernel<13,8,16,168,...,UPAR> (launch-uniform parameters: member constants as constant-bank "
+              "operands; ensembles with per-member parameters take the table-driven / per-member-coefficient instances)"
+              if workload == "classic" else "miz_fast_kernel<6>")
     return {"bound": "fp64", "achieved": res["achieved_tflops"], "peak": env.peak_tf, "unit": "TFLOP/s", "frac": frac,
             "traffic": traffic.get(workload, {}).get("bytes") if traffic else None,
             "traffic_source": traffic.get(workload, {}).get("source") if traffic else None,

@@ -16,7 +16,8 @@ from . import _lib
 from .types import (CLASSIC_PAR_ORDER, CLASSIC_VARS, MIZ_PAR_ORDER, MIZ_VARS, Collection, Forcing, Solutions,
                     SpaceTime)
 
-__all__ = ["integrate", "integrate_ensemble", "integrate_arrays", "step", "EnsembleResult", "fp64_peak", "model_name"]
+__all__ = ["integrate", "integrate_ensemble", "integrate_arrays", "integrate_grids", "GroupedResult", "step", "EnsembleResult",
+           "fp64_peak", "model_name"]
 
 _MIZ_STATE = ("Ei", "Ew", "h", "D", "phi")
 _CLASSIC_STATE = ("E", "Tg")
@@ -100,6 +101,54 @@ def integrate_ensemble(model, st: SpaceTime, forcings, pars, inits, *, T0guess=N
         if T0guess is not None:
             state["T0"] = np.asarray(T0guess, dtype=np.float64).reshape(nmem, st.nx)
     return integrate_arrays(name, st, forc, par, state, **kw)
+
+
+@dataclass
+class GroupedResult:
+    """Result of ``integrate_grids``: one ``EnsembleResult`` per distinct SpaceTime, plus where each member went."""
+    groups: list            # [(SpaceTime, member indices in the caller's order, EnsembleResult)]
+    where: list             # member m -> (group index, row inside the group)
+
+    def member(self, m: int) -> dict:
+        """diag [dur, 3, 4], final state {name: [nx]}, flags of member m (caller's numbering)."""
+        g, r = self.where[m]
+        st, _, res = self.groups[g]
+        out = {"spacetime": st, "diag": None if res.diag is None else res.diag[r],
+               "final": {k: v[r] for k, v in res.final.items()}, "flags": None if res.flags is None else int(res.flags[r])}
+        if res.newton_iters is not None:
+            out["newton_iters"] = int(res.newton_iters[r])
+        return out
+
+
+def integrate_grids(model, sts, forcings, pars, inits, **kw) -> GroupedResult:
+    """Ensemble whose members do not share one grid (per-member nx / nt / duration / grid kind): ``sts[m]`` is
+    member m's SpaceTime.  Members are grouped by SpaceTime -- a kernel launch integrates one grid: the latitude
+    tables, the band partition and the time loop are per launch -- each group is one ``integrate_ensemble`` call, and
+    the results are addressed by the caller's member index.  A member's result depends only on its own inputs, so it is
+    bit-identical to integrating that member alone."""
+    nmem = len(sts)
+    if not (len(forcings) == nmem == len(pars) == len(inits)) or nmem == 0:
+        raise ValueError("sts, forcings, pars and inits must be non-empty and of equal length")
+    if kw.get("field_stride", 0) not in (0, 1):
+        raise ValueError("integrate_grids: field_stride must be 0 or 1 (field output is selected per group)")
+    keys, order = {}, []
+    for m, st in enumerate(sts):
+        key = (st.nx, st.nt, st.dur, st.grid_kind)
+        if key not in keys:
+            keys[key] = len(order)
+            order.append((st, []))
+        order[keys[key]][1].append(m)
+    groups, where = [], [None] * nmem
+    for g, (st, idx) in enumerate(order):
+        T0 = kw.get("T0guess")
+        kwg = dict(kw)
+        if T0 is not None:
+            kwg["T0guess"] = np.stack([np.asarray(T0[m], dtype=np.float64) for m in idx])
+        res = integrate_ensemble(model, st, [forcings[m] for m in idx], [pars[m] for m in idx], [inits[m] for m in idx], **kwg)
+        groups.append((st, idx, res))
+        for r, m in enumerate(idx):
+            where[m] = (g, r)
+    return GroupedResult(groups, where)
 
 
 def integrate_arrays(model, st: SpaceTime, forc, par, state, *, lastonly: bool = True, field_stride: int = 0,

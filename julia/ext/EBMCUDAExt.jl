@@ -162,6 +162,34 @@ function integrate(model::Symbol, st::SpaceTime{F}, forcings::AbstractVector{<:F
     return sols, (; diag, final, flags, stats...)
 end
 
+"""
+    integrate(model, sts::Vector{<:SpaceTime}, forcings, pars, inits; kwargs...) -> Vector{Tuple{Vector{Solutions},NamedTuple}}, where
+
+Members on different grids (per-member `nx`, `nt`, `dur`, grid function; SURVEY 8f-4): `sts[m]` is member m's SpaceTime.
+Members are grouped by SpaceTime (one kernel launch integrates one grid), each group is one ensemble call; the second
+return value maps member m to `(group, row)`.  A member's result is bit-identical to integrating it alone.
+"""
+function integrate(model::Symbol, sts::AbstractVector{<:SpaceTime}, forcings::AbstractVector{<:Forcing},
+                   pars::AbstractVector{Collection{Float64}}, inits::AbstractVector{Collection{Vec}}; kwargs...)
+    nmem = length(sts)
+    (nmem > 0 && length(forcings) == nmem == length(pars) == length(inits)) ||
+        throw(ArgumentError("sts, forcings, pars, inits must have equal non-zero length"))
+    keyof(st) = (st.nx, st.nt, st.dur, grid_kind(st), typeof(st))
+    order = Vector{Tuple{Any,Vector{Int}}}()
+    slot = Dict{Any,Int}()
+    for (m, st) in enumerate(sts)
+        k = keyof(st)
+        haskey(slot, k) || (push!(order, (st, Int[])); slot[k] = length(order))
+        push!(order[slot[k]][2], m)
+    end
+    where = Vector{Tuple{Int,Int}}(undef, nmem)
+    results = map(enumerate(order)) do (g, (st, idx))
+        for (r, m) in enumerate(idx); where[m] = (g, r); end
+        integrate(model, st, forcings[idx], pars[idx], inits[idx]; kwargs...)
+    end
+    return results, where
+end
+
 # single member on the GPU: same signature as the reference plus a trailing Val(:CUDA) so the CPU method stays reachable
 function integrate(model::Symbol, st::SpaceTime, forcing::Forcing, par::Collection{Float64}, init::Collection{Vec},
                    ::Val{:CUDA}; kwargs...)

@@ -453,3 +453,28 @@ def test_generic_stencil_extension(xfunc, nx):
         od = oracle_classic(st, forcings[:4], pars[:4], inits[:4])
         rd = ebm.integrate_arrays("Classic", st, forcing_rows(forcings[:4]), classic_rows(pars[:4]), {k: v[:4] for k, v in state.items()})
         assert_close(rd.final["E"], od["E"], tol, "default stencil")
+
+
+def test_integrate_grids_per_member_grids():
+    """SURVEY 8f-4, second half: members on different grids (nx, nt, duration) in one call.  integrate_grids groups the
+    members by SpaceTime (a launch integrates one grid) and addresses the results by the caller's member index; a
+    member's result is bit-identical to integrating it alone, and within tolerance of the oracle."""
+    p = ebm.default_parameters("Classic")
+    specs = [(100, 2000, 1), (60, 1000, 2), (100, 2000, 1), (150, 2000, 1), (60, 1000, 2), (37, 500, 1)]
+    sts = [ebm.SpaceTime(nx, nt, dur) for nx, nt, dur in specs]
+    forcings = [ebm.Forcing(-6.0 + 3.0 * m) for m in range(len(specs))]
+    pars = [p] * len(specs)
+    inits = [ebm.Collection(E=np.full(st.nx, 98.0 if m % 2 == 0 else -9.5), Tg=np.full(st.nx, 10.0 if m % 2 == 0 else -10.0))
+             for m, st in enumerate(sts)]
+    res = ebm.integrate_grids("Classic", sts, forcings, pars, inits)
+    assert len(res.groups) == 4 and [len(g[1]) for g in res.groups] == [2, 2, 1, 1]
+    for m, st in enumerate(sts):
+        one = ebm.integrate_ensemble("Classic", st, [forcings[m]], [pars[m]], [inits[m]])
+        got = res.member(m)
+        assert got["spacetime"] is st and got["diag"].shape == (st.dur, 3, 4)
+        for k in ("E", "Tg"):
+            assert np.array_equal(got["final"][k], one.final[k][0]), (m, k)
+        assert np.array_equal(got["diag"], one.diag[0], equal_nan=True)
+        o = oracle_classic(st, [forcings[m]], [pars[m]], [inits[m]])
+        tol = 1e-9 if st.nx <= 100 else 1e-8
+        assert_close(got["final"]["E"], o["E"][0], tol, f"member {m} E")

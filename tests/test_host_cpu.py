@@ -317,3 +317,35 @@ int main(void) { printf("%zu %zu %zu %zu %zu %zu\n", sizeof(ebm_multi_t), offset
         assert ei.value.code == _lib.EBM_ERR_CUDA
     with pytest.raises(ValueError):   # a device listed twice never reaches the library
         _lib.make_multi(devices=[0, 0])
+
+
+def test_integrate_grids_groups_members_by_spacetime(monkeypatch):
+    """SURVEY 8f-4 (per-member nx / nt): host-side grouping of integrate_grids with the device call stubbed out -- one
+    call per distinct SpaceTime, members of a group in the caller's order, results addressed by the caller's index."""
+    import sys
+    integ = sys.modules[ebm.integrate_grids.__module__]   # the module (the package re-exports the function `integrate`)
+    calls = []
+
+    def fake(model, st, forcings, pars, inits, **kw):
+        calls.append((st.nx, st.nt, st.dur, [f.base for f in forcings]))
+        n = len(pars)
+        return integ.EnsembleResult(model, st, n, 0, ("E", "T", "h"),
+                                    diag=np.array([[[[f.base] * 4] * 3] * st.dur for f in forcings]),
+                                    final={"E": np.stack([i["E"] + 1.0 for i in inits])}, flags=np.zeros(n, np.int32))
+    monkeypatch.setattr(integ, "integrate_ensemble", fake)
+    p = ebm.default_parameters("Classic")
+    specs = [(100, 2000, 1), (60, 1000, 2), (100, 2000, 1), (100, 2000, 3), (60, 1000, 2)]
+    sts = [ebm.SpaceTime(*s) for s in specs]
+    forcings = [ebm.Forcing(float(m)) for m in range(5)]
+    inits = [ebm.Collection(E=np.full(st.nx, float(m)), Tg=np.zeros(st.nx)) for m, st in enumerate(sts)]
+    res = ebm.integrate_grids("Classic", sts, forcings, [p] * 5, inits)
+    assert calls == [(100, 2000, 1, [0.0, 2.0]), (60, 1000, 2, [1.0, 4.0]), (100, 2000, 3, [3.0])]
+    assert res.where == [(0, 0), (1, 0), (0, 1), (2, 0), (1, 1)]
+    for m, st in enumerate(sts):
+        got = res.member(m)
+        assert got["diag"].shape == (st.dur, 3, 4) and got["diag"][0, 0, 0] == float(m)
+        assert got["final"]["E"].shape == (st.nx,) and got["final"]["E"][0] == m + 1.0 and got["flags"] == 0
+    with pytest.raises(ValueError):
+        ebm.integrate_grids("Classic", sts[:2], forcings, [p] * 5, inits)
+    with pytest.raises(ValueError):
+        ebm.integrate_grids("Classic", sts, forcings, [p] * 5, inits, field_stride=4)
