@@ -22,7 +22,7 @@ _i64p = C.POINTER(C.c_int64)
 # every symbol include/ebm_cuda.h declares
 EXPORTED_SYMBOLS = (
     "ebm_version", "ebm_last_error", "ebm_device_count", "ebm_launch_count", "ebm_shutdown",
-    "ebm_classic_run", "ebm_classic_run_device", "ebm_classic_step",
+    "ebm_classic_run", "ebm_classic_run_device", "ebm_classic_step", "ebm_classic_step_debug",
     "ebm_miz_run", "ebm_miz_run_device", "ebm_miz_step",
     "ebm_transpose_device", "ebm_fp64_peak", "ebm_classic_run_multi", "ebm_miz_run_multi",
 )
@@ -96,6 +96,8 @@ def load():
     lib.ebm_classic_run_device.argtypes = [C.POINTER(Grid), C.POINTER(ClassicDeviceArgs), C.POINTER(Options), C.c_void_p]
     lib.ebm_classic_step.restype = C.c_int32
     lib.ebm_classic_step.argtypes = [C.POINTER(Grid), _dp, C.c_int32, C.c_double, _dp, _dp, _dp, _dp]
+    lib.ebm_classic_step_debug.restype = C.c_int32
+    lib.ebm_classic_step_debug.argtypes = [C.POINTER(Grid), _dp, C.c_int32, C.c_double, _dp, _dp, _dp, _dp, C.c_int32, _dp]
     lib.ebm_miz_run.restype = C.c_int32
     lib.ebm_miz_run.argtypes = [C.POINTER(Grid), C.c_int64, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, C.POINTER(Options), C.POINTER(MizOutputs)]
     lib.ebm_miz_run_device.restype = C.c_int32

@@ -42,7 +42,7 @@ __device__ __forceinline__ ClassicStatics make_statics(const double* p, long lon
 __device__ void classic_step_literal(const EbmGridTables& g, const double* p, long long pstride,
                                      const ClassicStatics& s, int ti, double f,
                                      double* E, double* Tg, double* Tout, double* dg, double* y, double* w,
-                                     long long stride) {
+                                     long long stride, int dbg_which = 0, double* dbg = nullptr) {
   const int nx = g.nx;
   const double A = p[1 * pstride], cw = p[3 * pstride], S0 = p[4 * pstride], S1 = p[5 * pstride];
   const double S2 = p[6 * pstride], a0 = p[7 * pstride], a2 = p[8 * pstride], ai = p[9 * pstride];
@@ -65,6 +65,9 @@ __device__ void classic_step_literal(const EbmGridTables& g, const double* p, lo
     Ej = Lit::add(Ej, Lit::mul(s.dt, Lit::add(Lit::sub(C, Lit::mul(s.M, Tj)), Fb)));     // :53
     E[j * stride] = Ej;
     const bool mk = (T0 < 0.0) && (Ej < 0.0);
+    if (dbg != nullptr)   // debug menu of the step seam (include/ebm_cuda.h EBM_DEBUG_*; classic.jl:67-69)
+      dbg[j * stride] = dbg_which == EBM_DEBUG_ALPHA ? alpha : dbg_which == EBM_DEBUG_C ? C : dbg_which == EBM_DEBUG_T0 ? T0
+                      : dbg_which == EBM_DEBUG_S ? Si : dbg_which == EBM_DEBUG_MASK ? (mk ? 1.0 : 0.0) : nan("");
     const double gg = Lit::sub(s.M, Lit::div(s.kLf, Ej));
     // kappa diagonal: (1+dt_tau) - ((dt*D)*diffop_jj)/cg, diffop_jj = -l3, l3 = -l1 - l2 (infrastructure.jl:485-488)
     const double l1 = j > 0 ? -g.lam_lo[j] : 0.0, l2 = j < nx - 1 ? -g.lam_hi[j] : 0.0;
@@ -179,10 +182,11 @@ __global__ void classic_strict_kernel(const ClassicKArgs a, double* ws) {
 
 // one step, one member: contiguous [nx] arrays (stride 1); scratch = 3*nx doubles
 __global__ void classic_single_step_kernel(EbmGridTables g, const double* par15, int ti, double f,
-                                           double* E, double* Tg, double* T, double* h, double* scratch) {
+                                           double* E, double* Tg, double* T, double* h, double* scratch,
+                                           int dbg_which, double* dbg) {
   if (blockIdx.x != 0 || threadIdx.x != 0) return;
   const ClassicStatics s = make_statics(par15, 1, g.nt);
-  classic_step_literal(g, par15, 1, s, ti, f, E, Tg, T, scratch, scratch + g.nx, scratch + 2 * g.nx, 1);
+  classic_step_literal(g, par15, 1, s, ti, f, E, Tg, T, scratch, scratch + g.nx, scratch + 2 * g.nx, 1, dbg_which, dbg);
   const double Lf = par15[12];
   for (int j = 0; j < g.nx; ++j) h[j] = E[j] < 0.0 ? Lit::div(-E[j], Lf) : 0.0;  // classic.jl:65
 }
@@ -204,10 +208,11 @@ int ebm_launch_classic_strict(const ClassicKArgs& a, cudaStream_t stream) {
 }
 
 int ebm_launch_classic_single_step(const EbmGridTables& g, const double* par15, int ti, double f,
-                                   double* E, double* Tg, double* T, double* h, cudaStream_t stream) {
+                                   double* E, double* Tg, double* T, double* h, cudaStream_t stream,
+                                   int dbg_which, double* dbg) {
   double* scratch = nullptr;
   EBM_CUDA_TRY(cudaMallocAsync(&scratch, sizeof(double) * 3 * (size_t)g.nx, stream));
-  classic_single_step_kernel<<<1, 32, 0, stream>>>(g, par15, ti, f, E, Tg, T, h, scratch);
+  classic_single_step_kernel<<<1, 32, 0, stream>>>(g, par15, ti, f, E, Tg, T, h, scratch, dbg_which, dbg);
   cudaError_t e = cudaGetLastError();
   cudaFreeAsync(scratch, stream);
   EBM_CUDA_TRY(e);

@@ -516,11 +516,15 @@ extern "C" int32_t ebm_classic_run(const ebm_grid_t* grid, int64_t nmem, const e
   return EBM_OK;
 }
 
-extern "C" int32_t ebm_classic_step(const ebm_grid_t* grid, const ebm_classic_params_t* par, int32_t ti, double f,
-                                    double* E, double* Tg, double* T, double* h) {
+extern "C" int32_t ebm_classic_step_debug(const ebm_grid_t* grid, const ebm_classic_params_t* par, int32_t ti, double f,
+                                          double* E, double* Tg, double* T, double* h, int32_t which, double* debug_out) {
   EBM_TRY(check_grid(grid));
   if (!par || !E || !Tg || !T || !h) { ebm_set_error("classic_step: NULL argument"); return EBM_ERR_INVALID; }
   if (ti < 1 || ti > grid->nt) { ebm_set_error("classic_step: ti=%d outside 1..nt", ti); return EBM_ERR_INVALID; }
+  if (which < EBM_DEBUG_NONE || which > EBM_DEBUG_MASK || (which != EBM_DEBUG_NONE && !debug_out)) {
+    ebm_set_error("classic_step_debug: `which` must be one of EBM_DEBUG_* (the device cannot evaluate a debug::Expr) and debug_out non-NULL");
+    return which < EBM_DEBUG_NONE || which > EBM_DEBUG_MASK ? EBM_ERR_UNSUPPORTED : EBM_ERR_INVALID;
+  }
   ebm_options_t opt = default_options();
   DeviceRestore _dr;
   EBM_TRY(select_device(opt));
@@ -529,17 +533,23 @@ extern "C" int32_t ebm_classic_step(const ebm_grid_t* grid, const ebm_classic_pa
   EBM_TRY(get_tables(grid, &tabs, 0));
   DevBufs B;
   double* d = nullptr;
-  EBM_TRY(B.alloc(&d, (size_t)EBM_CLASSIC_NPAR + 4 * nx));
-  double *dpar = d, *dE = d + EBM_CLASSIC_NPAR, *dTg = dE + nx, *dT = dTg + nx, *dh = dT + nx;
+  EBM_TRY(B.alloc(&d, (size_t)EBM_CLASSIC_NPAR + 5 * nx));
+  double *dpar = d, *dE = d + EBM_CLASSIC_NPAR, *dTg = dE + nx, *dT = dTg + nx, *dh = dT + nx, *ddbg = dh + nx;
   EBM_CUDA_TRY(cudaMemcpy(dpar, par, sizeof(double) * EBM_CLASSIC_NPAR, cudaMemcpyHostToDevice));
   EBM_CUDA_TRY(cudaMemcpy(dE, E, sizeof(double) * nx, cudaMemcpyHostToDevice));
   EBM_CUDA_TRY(cudaMemcpy(dTg, Tg, sizeof(double) * nx, cudaMemcpyHostToDevice));
-  EBM_TRY(ebm_launch_classic_single_step(tabs, dpar, ti, f, dE, dTg, dT, dh, 0));
+  EBM_TRY(ebm_launch_classic_single_step(tabs, dpar, ti, f, dE, dTg, dT, dh, 0, which, which != EBM_DEBUG_NONE ? ddbg : nullptr));
   EBM_CUDA_TRY(cudaMemcpy(E, dE, sizeof(double) * nx, cudaMemcpyDeviceToHost));
   EBM_CUDA_TRY(cudaMemcpy(Tg, dTg, sizeof(double) * nx, cudaMemcpyDeviceToHost));
   EBM_CUDA_TRY(cudaMemcpy(T, dT, sizeof(double) * nx, cudaMemcpyDeviceToHost));
   EBM_CUDA_TRY(cudaMemcpy(h, dh, sizeof(double) * nx, cudaMemcpyDeviceToHost));
+  if (which != EBM_DEBUG_NONE) EBM_CUDA_TRY(cudaMemcpy(debug_out, ddbg, sizeof(double) * nx, cudaMemcpyDeviceToHost));
   return EBM_OK;
+}
+
+extern "C" int32_t ebm_classic_step(const ebm_grid_t* grid, const ebm_classic_params_t* par, int32_t ti, double f,
+                                    double* E, double* Tg, double* T, double* h) {
+  return ebm_classic_step_debug(grid, par, ti, f, E, Tg, T, h, EBM_DEBUG_NONE, nullptr);
 }
 
 // ----------------------------------------------------------------------------- MIZ

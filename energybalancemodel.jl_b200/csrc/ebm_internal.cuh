@@ -106,7 +106,8 @@ int ebm_classic_uniform_max_nx();
 int ebm_classic_uniform_slots();   // resident CTAs of the production kernel on the current device (wave balancing)
 int ebm_launch_classic_strict(const ClassicKArgs& a, cudaStream_t stream);
 int ebm_launch_classic_single_step(const EbmGridTables& g, const double* par15, int ti, double f,
-                                   double* E, double* Tg, double* T, double* h, cudaStream_t stream);
+                                   double* E, double* Tg, double* T, double* h, cudaStream_t stream,
+                                   int dbg_which = 0, double* dbg = nullptr);   // dbg: device [nx] or NULL (EBM_DEBUG_*)
 int ebm_launch_miz(const MizKArgs& a, int strict, cudaStream_t stream);
 int ebm_launch_miz_fast(const MizKArgs& a, cudaStream_t stream);     // miz_kernel.cu
 int ebm_launch_miz_strict(const MizKArgs& a, cudaStream_t stream);   // miz_strict.cu (-fmad=false)

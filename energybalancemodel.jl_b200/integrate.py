@@ -252,13 +252,22 @@ def integrate(model, st: SpaceTime, forcing: Forcing, par: Collection, init: Col
     return sols
 
 
-def step(model, t: float, f: float, vars: Collection, st: SpaceTime, par: Collection) -> Collection:
-    """``step!(Val(model), t, f, vars, st, par)``: one time step of one member, in place, on the GPU.
+DEBUG_MENU = {"alpha": 1, "C": 2, "T0": 3, "S": 4, "mask": 5}   # include/ebm_cuda.h EBM_DEBUG_*
+
+
+def step(model, t: float, f: float, vars: Collection, st: SpaceTime, par: Collection, *, debug=None) -> Collection:
+    """``step!(Val(model), t, f, vars, st, par; debug)``: one time step of one member, in place, on the GPU.
 
     For ``:MIZ`` the closure's warm start (the reference's persistent ``T0``, src/miz.jl:47) is carried
-    in ``vars.T0`` (zeros if absent).
+    in ``vars.T0`` (zeros if absent).  ``debug`` (``:Classic``): the reference evaluates an arbitrary expression in
+    the scope of step! and stores it as ``vars.debug`` (src/classic.jl:67-69); here it is the name of one of the
+    per-cell locals of that scope -- ``"alpha"``, ``"C"``, ``"T0"``, ``"S"`` (= stat.S[:, i]), ``"mask"`` -- anything
+    else is an error (an expression cannot run on the device).
     """
     name = model_name(model)
+    if debug is not None and (name != "Classic" or debug not in DEBUG_MENU):
+        raise ValueError(f"debug must be one of {sorted(DEBUG_MENU)} for :Classic (a `debug::Expr` cannot be evaluated "
+                         "on the device: EBM_ERR_UNSUPPORTED)")
     lib = _lib.load()
     grid = _lib.make_grid(st)
     # time index exactly as src/classic.jl:45
@@ -271,9 +280,13 @@ def step(model, t: float, f: float, vars: Collection, st: SpaceTime, par: Collec
         E = np.array(vars["E"], dtype=np.float64)
         Tg = np.array(vars["Tg"], dtype=np.float64)
         T, h = np.empty(nx), np.empty(nx)
-        _lib.check(lib.ebm_classic_step(C.byref(grid), _lib.dptr(p), ti, float(f), _lib.dptr(E), _lib.dptr(Tg),
-                                        _lib.dptr(T), _lib.dptr(h)))
+        dbg = np.empty(nx) if debug is not None else None
+        _lib.check(lib.ebm_classic_step_debug(C.byref(grid), _lib.dptr(p), ti, float(f), _lib.dptr(E), _lib.dptr(Tg),
+                                              _lib.dptr(T), _lib.dptr(h), DEBUG_MENU.get(debug, 0),
+                                              _lib.dptr(dbg) if dbg is not None else None))
         vars["E"], vars["Tg"], vars["T"], vars["h"] = E, Tg, T, h
+        if dbg is not None:
+            vars["debug"] = dbg
     else:
         # the reference's MIZ step! uses t itself (cos(2 pi t), src/miz.jl:11), not a table index: the device entry
         # point takes the index of t in st.t, so a t off the grid would silently get its neighbour's insolation

@@ -173,6 +173,13 @@ int32_t ebm_classic_run_device(const ebm_grid_t* grid, const ebm_classic_device_
  * 1-based index of t in st.t.  E, Tg in/out; T, h out; all [nx] host.  Uses the strict kernel.          */
 int32_t ebm_classic_step(const ebm_grid_t* grid, const ebm_classic_params_t* par, int32_t ti, double f,
                          double* E, double* Tg, double* T, double* h);
+/* the same step with a debug variable.  The reference evaluates an arbitrary `debug::Expr` in the scope of step!
+ * (src/classic.jl:67-69) and stores it as vars.debug; an expression cannot run on the device, so the seam offers the
+ * per-cell locals such expressions name as a fixed menu: debug_out [nx] receives the selected one
+ * (alpha :47, C :48, T0 :50, S = stat.S[:,i] :48, mask = (T0<0)&(E<0) :56 as 0/1).                       */
+enum { EBM_DEBUG_NONE = 0, EBM_DEBUG_ALPHA = 1, EBM_DEBUG_C = 2, EBM_DEBUG_T0 = 3, EBM_DEBUG_S = 4, EBM_DEBUG_MASK = 5 };
+int32_t ebm_classic_step_debug(const ebm_grid_t* grid, const ebm_classic_params_t* par, int32_t ti, double f,
+                               double* E, double* Tg, double* T, double* h, int32_t which, double* debug_out);
 
 /* ---- MIZ: integrate(:MIZ, ...) -- src/miz.jl:150-196 + closure :33-68 ----------------------------- */
 int32_t ebm_miz_run(const ebm_grid_t* grid, int64_t nmem, const ebm_miz_params_t* par,

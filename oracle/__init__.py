@@ -79,6 +79,28 @@ def diag(T, E, phi, x):
     return out
 
 
+DEBUG_MENU = {"alpha": 1, "C": 2, "T0": 3, "S": 4, "mask": 5}
+
+
+def classic_step(x, t, par15, i1, f, E, Tg, debug=None):
+    """One step!(Val(:Classic), ...) (src/classic.jl:37-71).  Returns dict(E, Tg, T, h[, debug]); inputs untouched."""
+    x, t = _c(x), _c(t)
+    nx = len(x)
+    E, Tg = _c(E, (nx,)).copy(), _c(Tg, (nx,)).copy()
+    T, h = np.empty(nx), np.empty(nx)
+    dbg = np.empty(nx) if debug is not None else None
+    fn = lib().ebm_oracle_classic_step
+    fn.restype = ctypes.c_int
+    rc = fn(nx, len(t), _p(x), _p(t), _p(_c(par15, (CLASSIC_NPAR,))), int(i1), ctypes.c_double(f), _p(E), _p(Tg), _p(T), _p(h),
+            DEBUG_MENU[debug] if debug is not None else 0, _p(dbg))
+    if rc != 0:
+        raise RuntimeError(f"oracle classic_step failed: {rc}")
+    out = dict(E=E, Tg=Tg, T=T, h=h)
+    if debug is not None:
+        out["debug"] = dbg
+    return out
+
+
 def classic_run(x, t, dur, winter_inx, summer_inx, par, forc, E0, Tg0, *, solver=SOLVE_TRIDIAG,
                 lastonly=True, want_raw=False, want_seasonal=False, nthreads=0, stencil=0):
     """Returns dict(E, Tg[, raw[nmem,nraw,3,nx]][, seasonal[nmem,dur,3,3,nx]]); inputs untouched.

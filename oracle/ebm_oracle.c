@@ -258,8 +258,16 @@ static void solve_dense_lu(int n, double* A, double* b) {
 
 /* step!(::Val{:Classic}), src/classic.jl:37-71.  i1 = 1-based index of t in the year (:45).
  * E, Tg updated in place; T, h written. */
+/* debug menu (ODBG_*): the locals of step! a `debug` expression of the reference usually names (classic.jl:67-69 evaluates
+ * an arbitrary expression in this scope; the menu offers the per-cell ones): dbg = NULL or [nx] */
+static void classic_step_dbg(const classic_statics* st, const double* p, int i1, double f,
+                             double* E, double* Tg, double* T, double* h, int solver, double* work, int which, double* dbg);
 static void classic_step(const classic_statics* st, const double* p, int i1, double f,
                          double* E, double* Tg, double* T, double* h, int solver, double* work) {
+  classic_step_dbg(st, p, i1, f, E, Tg, T, h, solver, work, 0, NULL);
+}
+static void classic_step_dbg(const classic_statics* st, const double* p, int i1, double f,
+                             double* E, double* Tg, double* T, double* h, int solver, double* work, int which, double* dbg) {
   const int nx = st->nx;
   const double* Si = st->S + (size_t)(i1 - 1) * nx;
   const double* Sn = st->S + (size_t)i1 * nx; /* column i+1 */
@@ -274,6 +282,8 @@ static void classic_step(const classic_statics* st, const double* p, int i1, dou
     Ej = Ej + st->dt * (C - st->M * Tj + p[OC_Fb]);                                           /* :53 */
     E[j] = Ej;
     int m = (T0 < 0.0) && (Ej < 0.0);          /* T0 from the OLD E, E already updated (:56,61) */
+    if (dbg) dbg[j] = which == ODBG_ALPHA ? alpha : which == ODBG_C ? C : which == ODBG_T0 ? T0 : which == ODBG_S ? Si[j]
+                    : which == ODBG_MASK ? (double)m : NAN;
     double g = st->M - st->kLf / Ej;
     diag[j] = st->kdiag[j] - (m ? st->dc / g : 0.0);                                          /* :56 */
     rhs[j] = Tg[j] + (st->dt_tau * ((Ej >= 0.0 ? Ej / p[OC_cw] : 0.0) +
@@ -292,6 +302,18 @@ static void classic_step(const classic_statics* st, const double* p, int i1, dou
   } else {
     solve_tridiag(nx, st->ksub, st->koff, diag, rhs, Tg, w, y);
   }
+}
+
+int ebm_oracle_classic_step(int nx, int nt, const double* x, const double* t, const double* par15, int i1, double f,
+                            double* E, double* Tg, double* T, double* h, int which, double* dbg) {
+  if (nx < 2 || nt < 1 || i1 < 1 || i1 > nt) return -1;
+  classic_statics st;
+  classic_statics_init(&st, nx, nt, x, t, par15, 0);
+  double* work = (double*)malloc(sizeof(double) * 4 * (size_t)nx);
+  classic_step_dbg(&st, par15, i1, f, E, Tg, T, h, OSOLVE_TRIDIAG, work, which, dbg);
+  free(work);
+  classic_statics_free(&st);
+  return 0;
 }
 
 int ebm_oracle_classic_run(int nx, int nt, int dur, const double* x, const double* t,

@@ -52,6 +52,12 @@ double ebm_oracle_forcing(const double* frow, double T);
  *   seasonal : NULL or [nmem][dur][3 (winter,summer,avg)][OCV_NVAR][nx]  (NaN where never stored)
  * returns 0 on success.
  */
+/* one step!(Val(:Classic), ...) of one member (src/classic.jl:37-71) with the debug menu: dbg = NULL or [nx] receives the
+ * step's local `which` (classic.jl:67-69 evaluates a user expression in that scope) */
+enum { ODBG_NONE = 0, ODBG_ALPHA = 1, ODBG_C = 2, ODBG_T0 = 3, ODBG_S = 4, ODBG_MASK = 5 };
+int ebm_oracle_classic_step(int nx, int nt, const double* x, const double* t, const double* par15, int i1, double f,
+                            double* E, double* Tg, double* T, double* h, int which, double* dbg);
+
 int ebm_oracle_classic_run(int nx, int nt, int dur, const double* x, const double* t,
                            int winter_inx, int summer_inx, int nmem,
                            const double* par, const double* forc,

@@ -79,8 +79,9 @@ def classic_statics(x, t, nt, par, stencil=0):
     return dict(dt=dt, cg_tau=cg_tau, dt_tau=dt_tau, dc=dc, kappa=kappa, S=S, M=M, aw=aw, kLf=kLf)
 
 
-def classic_step(stat, par, i, f, E, Tg):
-    """src/classic.jl:43-65; ``i`` is the 1-based year index.  Returns (E, Tg, T, h)."""
+def classic_step(stat, par, i, f, E, Tg, debug=None):
+    """src/classic.jl:43-65; ``i`` is the 1-based year index.  Returns (E, Tg, T, h), plus the local named by ``debug``
+    (the reference's `debug::Expr` is evaluated in this scope, :67-69)."""
     S = stat["S"]
     with np.errstate(all="ignore"):
         alpha = np.where(E > 0.0, stat["aw"], 0.0) + np.where(E < 0.0, par["ai"], 0.0)
@@ -95,6 +96,8 @@ def classic_step(stat, par, i, f, E, Tg):
                                      + np.where(mask, (par["ai"] * S[:, i] - par["A"] + f) / g, 0.0))
         Tg = np.linalg.solve(A, rhs)
         h = np.where(E < 0.0, -E / par["Lf"], 0.0)
+    if debug is not None:
+        return E, Tg, T, h, dict(alpha=alpha, C=C, T0=T0, S=S[:, i - 1], mask=mask.astype(float))[debug]
     return E, Tg, T, h
 
 

@@ -21,6 +21,26 @@ def _par(**kw):
     return p
 
 
+def test_single_step_debug_menu_bitwise():
+    """The `debug` seam of step! (src/classic.jl:67-69) as a fixed menu of the step's per-cell locals
+    (EBM_DEBUG_*: alpha, C, T0, S, mask): bit-identical to the oracle's locals; an expression is refused."""
+    import oracle
+    st = ebm.SpaceTime(100, 2000, 1)
+    par = _par()
+    row = [par[k] for k in ebm.CLASSIC_PAR_ORDER]
+    E0 = np.linspace(60.0, -25.0, 100)
+    E0[40] = 0.0                                      # alpha = 0 at E == 0, T0 = C / -Inf = -0.0
+    Tg0 = np.linspace(12.0, -14.0, 100)
+    for name in ("alpha", "C", "T0", "S", "mask"):
+        o = oracle.classic_step(st.x, st.t, row, 7, 1.25, E0, Tg0, debug=name)
+        v = ebm.Collection(E=E0.copy(), Tg=Tg0.copy())
+        ebm.step("Classic", st.t[6], 1.25, v, st, par, debug=name)
+        assert np.array_equal(v.debug, o["debug"]), name
+        assert np.array_equal(v.E, o["E"]) and np.array_equal(v.Tg, o["Tg"]) and np.array_equal(v.T, o["T"])
+    with pytest.raises(ValueError):
+        ebm.step("Classic", st.t[6], 1.25, ebm.Collection(E=E0.copy(), Tg=Tg0.copy()), st, par, debug="C .- T0")
+
+
 def test_single_step_bitwise():
     """step!(Val(:Classic), ...) one step: bit-identical to the oracle, warm and cold states."""
     st = ebm.SpaceTime(100, 2000, 1)

@@ -288,3 +288,25 @@ def test_classic_generic_stencil_extension():
         assert rel_err(r[v], c["raw"][0, :, vi]).max() < 1e-9, v
     ref_behaviour = oracle_classic(sts, [f], [par], [warm_init(60)])          # get_diffop on the sin grid: what the reference does
     assert np.abs(ref_behaviour["E"] - c["E"]).max() > 1.0                    # ... a different model
+
+
+def test_classic_step_debug_menu_matches_the_numpy_restatement():
+    """The oracle's debug menu (locals of step!, src/classic.jl:47-56, that a `debug::Expr` would name) against the
+    independent NumPy restatement, warm / cold / mixed states incl. E == 0."""
+    import np_restatement as npr
+    st = ebm.SpaceTime(100, 2000, 1)
+    par = ebm.default_parameters("Classic")
+    row = [par[k] for k in ebm.CLASSIC_PAR_ORDER]
+    stat = npr.classic_statics(st.x, st.t, st.nt, par)
+    E0 = np.linspace(60.0, -25.0, 100)
+    E0[40] = 0.0
+    Tg0 = np.linspace(12.0, -14.0, 100)
+    for i1, f in ((1, 0.0), (7, 1.25), (2000, -3.0)):
+        for name in oracle.DEBUG_MENU:
+            o = oracle.classic_step(st.x, st.t, row, i1, f, E0, Tg0, debug=name)
+            E, Tg, T, h, dbg = npr.classic_step(stat, par, i1, f, E0.copy(), Tg0.copy(), debug=name)
+            np.testing.assert_allclose(o["debug"], dbg, rtol=1e-13, atol=1e-13, err_msg=name)
+            np.testing.assert_allclose(o["E"], E, rtol=1e-13, atol=1e-12)
+            np.testing.assert_allclose(o["Tg"], Tg, rtol=1e-11, atol=1e-11)
+    o = oracle.classic_step(st.x, st.t, row, 7, 1.25, E0, Tg0, debug="alpha")
+    assert o["debug"][40] == 0.0 and set(np.unique(o["debug"][E0 < 0.0])) == {par["ai"]}
