@@ -499,3 +499,31 @@ def test_integrate_grids_per_member_grids():
         o = oracle_classic(st, [forcings[m]], [pars[m]], [inits[m]])
         tol = 1e-9 if st.nx <= 100 else 1e-8
         assert_close(got["final"]["E"], o["E"][0], tol, f"member {m} E")
+
+
+def test_launch_uniform_parameter_instance_is_bit_identical():
+    """A forcing sweep (every member has the same 15 parameters) takes the launch-uniform-parameter instance of the
+    kernel: member constants derived on the host and read as constant-bank operands.  Same bits as the per-member
+    instance (EBM_NO_UPAR=1), warm and cold starts, constant and ramp forcing, with field output."""
+    import os
+    nmem, nx = 96, 100
+    st = ebm.SpaceTime(nx, 2000, 2)
+    par = _par()
+    forcings = [ebm.Forcing(-18.0 + 36.0 * m / (nmem - 1)) if m % 5 else ebm.Forcing(-2.0, 6.0, 1.0, holdyrs=(0, 0), rates=(4.0, -5.0))
+                for m in range(nmem)]
+    inits = [warm_init(nx) if m % 2 == 0 else cold_init(nx) for m in range(nmem)]
+    runs = []
+    for flag in (None, "1"):
+        if flag is None:
+            os.environ.pop("EBM_NO_UPAR", None)
+        else:
+            os.environ["EBM_NO_UPAR"] = flag
+        try:
+            runs.append(ebm.integrate_ensemble("Classic", st, forcings, [par] * nmem, inits, field_stride=16))
+        finally:
+            os.environ.pop("EBM_NO_UPAR", None)
+    a, b = runs
+    for k in ("E", "Tg"):
+        assert np.array_equal(a.final[k], b.final[k]), k
+    assert np.array_equal(a.diag, b.diag, equal_nan=True)
+    assert np.array_equal(a.seasonal, b.seasonal, equal_nan=True) and np.array_equal(a.raw, b.raw, equal_nan=True)
