@@ -775,13 +775,19 @@ __global__ void __maxnreg__(MAXR) classic_uniform_kernel(const __grid_constant__
   double S1c_next = cS1 * __ldg(a.g.ctab);   // S1*cos(2*pi*t_1); ctab[nt] == ctab[0] closes the year (classic.jl:25)
   for (int year = a.year0; year < a.year0 + a.nyears; ++year) {
     const bool raw_year = has_raw && (!a.lastonly || year == a.dur - 1);
+#pragma unroll 1
     for (int ti = 1; ti <= nt; ++ti) {
+      // The loop carries `ti` and `year` only: an opaque copy of the index keeps ptxas from expanding it into 64-bit
+      // induction variables (table pointer, global step number), which it then spilled -- 8 local-memory instructions in a
+      // dependent chain at the end of every step.
+      int tix = ti;
+      asm volatile("" : "+r"(tix));
       // column i+1 of this step is column i of the next: one table load per step, consumed late in the step
-      const double S1c0 = S1c_next, S1c1 = cS1 * __ldg(a.g.ctab + ti);
+      const double S1c0 = S1c_next, S1c1 = cS1 * __ldg(a.g.ctab + tix);
       S1c_next = S1c1;
       double f = fbase;
       if (!constf) {
-        const long long tinx = (long long)(year + a.start_year) * nt + ti;
+        const long long tinx = (long long)(year + a.start_year) * nt + tix;
         f = ebm_forcing_eval(fr[0 * MW + mi], fr[1 * MW + mi], fr[2 * MW + mi], fr[3 * MW + mi], fr[4 * MW + mi],
                              fr[6 * MW + mi], fr[7 * MW + mi], fr[8 * MW + mi], fr[9 * MW + mi],
                              ebm_global_time(tinx, nt));
