@@ -166,7 +166,9 @@ int32_t ebm_shutdown(void);
 int32_t ebm_classic_run(const ebm_grid_t* grid, int64_t nmem, const ebm_classic_params_t* par,
                         const ebm_forcing_t* forc, const double* E0, const double* Tg0,
                         const ebm_options_t* opt, ebm_classic_outputs_t* out);
-/* same, inputs resident in HBM; enqueues on `stream` (cudaStream_t) and returns without synchronising */
+/* same, inputs resident in HBM; enqueues on `stream` (cudaStream_t) and returns without waiting for the integration.
+ * (nx <= 104: a 124-byte read-back at entry -- are the 15 parameters the same for every member? -- waits for work
+ * queued earlier on `stream`; such ensembles take the kernel instance with the member constants in the argument block.) */
 int32_t ebm_classic_run_device(const ebm_grid_t* grid, const ebm_classic_device_args_t* args,
                                const ebm_options_t* opt, void* stream);
 /* one step of one member, step!(Val(:Classic), t, f, vars, st, par) (src/classic.jl:37-71); `ti` is the

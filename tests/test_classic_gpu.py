@@ -226,6 +226,33 @@ def test_c4_members_two_hundred_years():
     assert area.min() < 0.5 and area.max() > 6.0
 
 
+def test_c4_sweep_two_thousand_members_two_years():
+    """BASELINE config C4 at width: every 32nd member of the 65 536-member hysteresis sweep (2048 members, both
+    branches, F = -20..+20) through the launch-uniform-parameter instance, two years from the sweep's initial states
+    (freeze-up of the cold branch, melt-back of the warm one): final state and every diagnostic against the oracle at
+    the stated tolerance, member by member; flagged samples (enthalpy within 1e-6 of the branch threshold, or ice mask
+    differing from the oracle's) are counted and must be rare."""
+    N, H, stride = 65536, 32768, 32
+    idx = list(range(0, N, stride))
+    nsub = len(idx)
+    st = ebm.SpaceTime(100, 2000, 2)
+    par = _par()
+    forcings = [ebm.Forcing(-20.0 + 40.0 * (m // 2) / (H - 1)) for m in idx]
+    inits = [warm_init(100) if (m // stride) % 2 == 0 else cold_init(100) for m in idx]   # idx is even: alternate the branch
+    o = oracle_classic(st, forcings, [par] * nsub, inits, seasonal=True)
+    r = ebm.integrate_ensemble("Classic", st, forcings, [par] * nsub, inits)
+    assert r.flags.max() == 0
+    fE = (np.abs(o["E"]) < 1e-6) | ((r.final["E"] < 0) != (o["E"] < 0))
+    nflag = assert_close(r.final["E"], o["E"], TOL, "final E after 2 y", flag=fE)
+    assert_close(r.final["Tg"], o["Tg"], TOL, "final Tg after 2 y")
+    od = oracle_diag_classic(o["seasonal"], st.x)
+    assert_close(r.diag[..., :2], od[..., :2], TOL, "mean T / mean E, both years, three seasons")
+    near0 = (np.abs(o["seasonal"][:, :, :, 0, :]) < 1e-9).any(axis=-1)
+    mism = (np.abs(r.diag[..., 2:] - od[..., 2:]) > 1e-9).any(axis=-1)
+    assert not (mism & ~near0).any()
+    print(f"C4 sample: {nsub} members x 2 y, {nflag} flagged cells of {fE.size}; ice area range {r.diag[:, -1, 2, 2].min():.2f}..{r.diag[:, -1, 2, 2].max():.2f}")
+
+
 def test_sweep_of_non_matrix_parameters_takes_the_table_driven_kernel():
     """A, B, cw, S1, ai, Fb, k, Lf may differ per member inside a 32-member group of the fast (table-driven) kernel --
     only D, cg, tau, S0, S2, a0, a2 build its shared tables.  70 members sweeping B, A, ai, k and the forcing."""
