@@ -192,7 +192,7 @@ __device__ __forceinline__ void tridiag(int lane, RowFn row, double (&rhs)[K]) {
 #pragma unroll
   for (int st = 1; st < 32; st <<= 1) {
     // couplings shrink quadratically (products of 2^k original ones): the last steps are usually no-ops
-    if (st >= 8 && !__any_sync(kFull, fabs(A) + fabs(C) > 1e-19)) break;
+    if (st >= 4 && !__any_sync(kFull, fabs(A) + fabs(C) > 1e-19)) break;
     const double Au = __shfl_up_sync(kFull, A, st), Cu = __shfl_up_sync(kFull, C, st), Ru = __shfl_up_sync(kFull, R, st);
     const double Ad = __shfl_down_sync(kFull, A, st), Cd = __shfl_down_sync(kFull, C, st), Rd = __shfl_down_sync(kFull, R, st);
     const double a_ = (lane >= st) ? A : 0.0, c_ = (lane + st < 32) ? C : 0.0;
