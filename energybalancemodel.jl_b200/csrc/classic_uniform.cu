@@ -367,13 +367,13 @@ struct Ctx {
 
     // ---- physics (classic.jl:47-53) and the rows of the implicit system (:55-63)
     // One code path per warp (a warp whose lanes disagree would run both, one after the other): the open-water code
-    // below only if no lane holds an ice cell or a cell about to freeze (E < 1/4: signed compare of the high words --
-    // |dE| per step is ~dt * 300), else the ice code for every lane.  Both give the same bits for an open-water cell
+    // below only if no lane holds an ice cell or a cell about to freeze (E < 512 dt, a.hthr: signed compare of the high
+    // words -- |dE| per step is ~dt * 300), else the ice code for every lane.  Both give the same bits for an open-water cell
     // that stays open water, so the result does not depend on which members share a warp.
     int hmin = 0x7fffffff;
 #pragma unroll
     for (int i = 0; i < K; ++i) hmin = min(hmin, __double2hiint(E[i]));
-    const bool has_ice = __any_sync(0xffffffffu, hmin < 0x3fd00000);
+    const bool has_ice = __any_sync(0xffffffffu, hmin < a.hthr);
     if (!has_ice) {
       bool crossed = false;
       double se[K];                                         // annual sums: loaded up front, stored after the loop, so
@@ -396,7 +396,7 @@ struct Ctx {
       }
 #pragma unroll
       for (int i = 0; i < K; ++i) sumE[cidx(i)] = se[i];
-      if (crossed) {   // freeze-up of a cell with E >= 1/4 inside one step (never at the reference's step sizes): literal mask
+      if (crossed) {   // freeze-up of a cell with E >= 512 dt inside one step (a tendency beyond 512 W/m^2: safety net): literal mask
 #pragma unroll
         for (int i = 0; i < K; ++i) rs.q(i) = 0.0;
 #pragma unroll

@@ -304,6 +304,11 @@ extern "C" int32_t ebm_classic_run_device(const ebm_grid_t* grid, const ebm_clas
   a.diag = args->diag; a.seasonal = args->seasonal; a.raw = args->raw; a.flags = args->flags;
   a.orig = (const long long*)args->member_index;
   a.dbg = getenv("EBM_DBG") ? atoi(getenv("EBM_DBG")) : 0;
+  {   // |dE| per step <= dt * |alpha S - A + f - B T + Fb| ~ dt * 300: cells above 512 dt stay open water for a step
+    const double ethr = 512.0 / (double)grid->nt;
+    long long bits; memcpy(&bits, &ethr, sizeof(bits));
+    a.hthr = (int)(bits >> 32);
+  }
   const int ypl = opt.years_per_launch > 0 ? opt.years_per_launch : grid->dur;
   static const int variant = getenv("EBM_CLASSIC_VARIANT") ? atoi(getenv("EBM_CLASSIC_VARIANT")) : 0;
   // ---- launch-uniform parameters (a forcing sweep such as C4: members differ in forcing and initial state only).  The

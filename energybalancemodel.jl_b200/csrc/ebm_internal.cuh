@@ -74,6 +74,7 @@ struct ClassicKArgs {
   double* diag; double* seasonal; double* raw; int* flags;
   const long long* orig;         // NULL or [nmem]: original member index of slot m (output rows, field selection)
   int dbg;                       // development switches (env EBM_DBG)
+  int hthr;                      // high word of 512/nt: an open-water cell with E above it cannot freeze within one step
   int upar;                      // 1: u is valid (every member of the launch shares all 15 parameters)
   ClassicUPar u;
   long long block0, nblocks;     // classic_uniform.cu: this launch covers the 16-member groups [block0, block0 + nblocks); nblocks 0 = all
