@@ -47,4 +47,15 @@ import EnergyBalanceModel: Vec
     sols, ens = integrate(:Classic, SpaceTime(100, 2000, 2), forcs, fill(parc, n), fill(initc, n); field_stride=16)
     @test length(sols) == 4 && size(ens.diag) == (4, 3, 2, n) && all(ens.flags .== 0)
     @test_throws ArgumentError integrate(:Classic, stc, forcs, fill(parc, n), fill(initc, n); debug=:(vars.E))
+
+    # --- members on different grids: grouped by SpaceTime, addressed by the caller's member index
+    sts = [SpaceTime(100, 2000, 1), SpaceTime(60, 1000, 2), SpaceTime(100, 2000, 1)]
+    inits3 = [Collection{Vec}(:E => fill(98.0, st.nx), :Tg => fill(10.0, st.nx)) for st in sts]
+    groups, where = integrate(:Classic, sts, forcs[1:3], fill(parc, 3), inits3; field_stride=1)
+    @test length(groups) == 2 && where == [(1, 1), (2, 1), (1, 2)]
+    for (m, st) in enumerate(sts)
+        g, r = where[m]
+        alone = integrate(:Classic, st, forcs[m], parc, inits3[m], Val(:CUDA))
+        @test groups[g][1][r].raw.E[end] == alone.raw.E[end]          # bit-identical to integrating the member alone
+    end
 end
